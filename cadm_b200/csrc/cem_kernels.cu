@@ -1,0 +1,292 @@
+// The small kernels around the rollout: CEM candidate sampling, particle mean, elite selection + refit,
+// context encoder, weight packing.  All are latency-bound helpers; the rollout kernel holds the FLOPs.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "rng.cuh"
+
+namespace cadm {
+
+// ------------------------------------------------------------------------------------------------
+// candidate action sequences
+// ------------------------------------------------------------------------------------------------
+// One value of a CEM candidate: mean + sqrt(constrained var) * z      (core/utils.py:131-135)
+__device__ __forceinline__ float cem_action_value(float mean, float var, float z) {
+    const float lb = mean - (-1.0f), ub = 1.0f - mean;
+    const float cvar = fminf(fminf((lb / 2.0f) * (lb / 2.0f), (ub / 2.0f) * (ub / 2.0f)), var);
+    return fmaf(sqrtf(cvar), z, mean);
+}
+
+
+__global__ void sample_actions_kernel(const SampleParams S) {
+    const int nb = (S.hA + 3) / 4;
+    const long long total = (long long)S.m * S.n_local * nb;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % nb);
+        const long long c = i / nb;
+        const int nl = (int)(c % S.n_local);
+        const int mi = (int)(c / S.n_local);
+        const int ng = S.n_offset + nl;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        const bool need_rng = (S.mode == 2) ? (S.u_int == nullptr) : (S.z == nullptr);
+        if (need_rng) {
+            const uint32_t stream = S.mode == 0 ? kStreamZ : (S.mode == 1 ? kStreamU : kStreamUD);
+            w = philox(S.seed, (uint32_t)j, (uint32_t)ng, (uint32_t)mi, ((uint32_t)S.it << 8) | stream);
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int k = 4 * j + l;
+            if (k >= S.hA) break;
+            const size_t o = ((size_t)mi * S.n_local + nl) * S.hA + k;
+            if (S.mode == 0) {
+                const float z = S.z ? S.z[((size_t)mi * S.n_global + ng) * S.hA + k] : trunc_normal(word_of(w, l));
+                S.actions[o] = cem_action_value(S.mean[(size_t)mi * S.hA + k], S.var[(size_t)mi * S.hA + k], z);
+            } else if (S.mode == 1) {
+                S.actions[o] = S.z ? S.z[o] : 2.0f * u01(word_of(w, l)) - 1.0f;
+            } else {
+                S.actions_int[o] = S.u_int ? S.u_int[o] : (int)(word_of(w, l) % (uint32_t)S.A);
+            }
+        }
+    }
+}
+
+cudaError_t launch_sample_actions(const SampleParams& S, cudaStream_t stream) {
+    const long long total = (long long)S.m * S.n_local * ((S.hA + 3) / 4);
+    const int threads = 256;
+    const int blocks = (int)min((total + threads - 1) / threads, (long long)148 * 8);
+    sample_actions_kernel<<<max(blocks, 1), threads, 0, stream>>>(S);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// mean over particles (core/utils.py:170), fixed summation order -> independent of the sharding
+// ------------------------------------------------------------------------------------------------
+__global__ void particle_mean_kernel(const float* __restrict__ ret_p, float* __restrict__ out, int count, int p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float* r = ret_p + (size_t)i * p;
+    float s = 0.f;
+    for (int k = 0; k < p; ++k) s += r[k];
+    out[i] = s / (float)p;
+}
+
+cudaError_t launch_particle_mean(const float* ret_p, float* out, int count, int p, cudaStream_t stream) {
+    particle_mean_kernel<<<(count + 255) / 256, 256, 0, stream>>>(ret_p, out, count, p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// elite selection + refit (core/utils.py:171-182); one CTA per environment
+// ------------------------------------------------------------------------------------------------
+
+// ascending-sortable key: larger return first, ties -> lower index first (tf.nn.top_k); NaN sorts last
+__device__ __forceinline__ unsigned long long elite_key(float v, int idx) {
+    if (v != v) v = -INFINITY;
+    if (v == 0.f) v = 0.f;          // -0 == +0
+    uint32_t u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending order of value
+    return ((unsigned long long)(~u) << 32) | (uint32_t)idx;
+}
+
+__global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
+    extern __shared__ unsigned long long keys[];      // [npad]
+    __shared__ int s_el[256];
+    const int mi = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n = R.n_global;
+    for (int i = tid; i < R.npad; i += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (i < n) {
+            const int g = i / R.n_local, nl = i - g * R.n_local;
+            const float v = R.returns_buf[((size_t)g * R.m + mi) * R.n_local + nl];
+            if (R.returns_log) R.returns_log[(size_t)mi * n + i] = v;
+            key = elite_key(v, i);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    // bitonic sort, ascending
+    for (int size = 2; size <= R.npad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < R.npad / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    if (R.mode_rs) {
+        if (tid == 0) R.best[mi] = (int)(keys[0] & 0xffffffffu);
+        return;
+    }
+    const int K = R.k_elites;
+    for (int i = tid; i < K; i += blockDim.x) {
+        const int idx = (int)(keys[i] & 0xffffffffu);
+        s_el[i] = idx;
+        if (R.elites_log) R.elites_log[(size_t)mi * K + i] = idx;
+    }
+    __syncthreads();
+    const int hA = R.h * R.A;
+    for (int k = tid; k < hA; k += blockDim.x) {
+        const float mu0 = R.mean[(size_t)mi * hA + k];
+        const float var0 = R.var[(size_t)mi * hA + k];
+        float sum = 0.f;
+        // pass 1: elite mean
+        for (int j = 0; j < K; ++j) {
+            const int ni = s_el[j];
+            float a;
+            if (ni >= R.n_offset && ni < R.n_offset + R.n_local) {
+                a = R.actions[((size_t)mi * R.n_local + (ni - R.n_offset)) * hA + k];
+            } else {
+                // not ours: regenerate from the counter-based stream (identical arithmetic on every rank)
+                float z;
+                if (R.z) z = R.z[((size_t)mi * n + ni) * hA + k];
+                else {
+                    uint4 w = philox(R.seed, (uint32_t)(k >> 2), (uint32_t)ni, (uint32_t)mi, ((uint32_t)R.it << 8) | kStreamZ);
+                    z = trunc_normal(word_of(w, k & 3));
+                }
+                a = cem_action_value(mu0, var0, z);
+            }
+            sum += a;
+        }
+        const float new_mean = sum / (float)K;
+        float sq = 0.f;
+        for (int j = 0; j < K; ++j) {
+            const int ni = s_el[j];
+            float a;
+            if (ni >= R.n_offset && ni < R.n_offset + R.n_local) {
+                a = R.actions[((size_t)mi * R.n_local + (ni - R.n_offset)) * hA + k];
+            } else {
+                float z;
+                if (R.z) z = R.z[((size_t)mi * n + ni) * hA + k];
+                else {
+                    uint4 w = philox(R.seed, (uint32_t)(k >> 2), (uint32_t)ni, (uint32_t)mi, ((uint32_t)R.it << 8) | kStreamZ);
+                    z = trunc_normal(word_of(w, k & 3));
+                }
+                a = cem_action_value(mu0, var0, z);
+            }
+            const float d = a - new_mean;
+            sq += d * d;
+        }
+        const float new_var = sq / (float)K;
+        R.mean[(size_t)mi * hA + k] = mu0 * R.alpha + (1.0f - R.alpha) * new_mean;
+        R.var[(size_t)mi * hA + k] = var0 * R.alpha + (1.0f - R.alpha) * new_var;
+    }
+}
+
+static int g_refit_smem = 0;
+cudaError_t launch_refit(const RefitParams& R, cudaStream_t stream) {
+    const size_t smem = (size_t)R.npad * 8;
+    if (smem > 48 * 1024 && (int)smem > g_refit_smem) {
+        cudaError_t e = cudaFuncSetAttribute(refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        g_refit_smem = (int)smem;
+    }
+    const int threads = R.npad / 2 >= 1024 ? 1024 : max(R.npad / 2, 256);
+    refit_kernel<<<R.m, threads, smem, stream>>>(R);
+    return cudaGetLastError();
+}
+
+// random shooting: gather the first action of the best candidate (core/utils.py:239-245)
+__global__ void rs_gather_kernel(const float* actions, const int* actions_int, const int* best, int n_local, int h, int A,
+                                 float* action, int* action_int) {
+    const int mi = blockIdx.x;
+    const int b = best[mi];
+    if (actions_int) {
+        if (threadIdx.x == 0 && action_int) action_int[mi] = actions_int[((size_t)mi * n_local + b) * h];
+    } else {
+        for (int a = threadIdx.x; a < A; a += blockDim.x)
+            if (action) action[(size_t)mi * A + a] = actions[(((size_t)mi * n_local + b) * h) * A + a];
+    }
+}
+
+cudaError_t launch_rs_gather(const float* actions, const int* actions_int, const int* best, int m, int n_local, int h,
+                             int A, float* action, int* action_int, cudaStream_t stream) {
+    rs_gather_kernel<<<m, 32, 0, stream>>>(actions, actions_int, best, n_local, h, A, action, action_int);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// context encoder (core/utils.py:400-407, 591-617): relu hidden layers, linear output; one CTA per (mi, e)
+// ------------------------------------------------------------------------------------------------
+
+__global__ void encoder_kernel(const EncoderParams Q) {
+    extern __shared__ float ebuf[];      // two ping-pong vectors of max width
+    const int mi = blockIdx.x, e = blockIdx.y;
+    int wmax = 0;
+    for (int l = 0; l <= Q.n_layers; ++l) wmax = max(wmax, Q.dims[l]);
+    float* x = ebuf;
+    float* y = ebuf + wmax;
+    const int no = Q.D * Q.K, na = Q.A * Q.K;
+    for (int i = threadIdx.x; i < no + na; i += blockDim.x) {
+        float v;
+        if (i < no) v = __fdiv_rn(Q.cp_obs[(size_t)mi * no + i] - Q.cpo_mean[i], Q.cpo_std[i] + 1e-10f);
+        else { const int a = i - no; v = __fdiv_rn(Q.cp_act[(size_t)mi * na + a] - Q.cpa_mean[a], Q.cpa_std[a] + 1e-10f); }
+        x[i] = v;
+    }
+    __syncthreads();
+    for (int l = 0; l < Q.n_layers; ++l) {
+        const int in = Q.dims[l], out = Q.dims[l + 1];
+        const float* W = Q.W[l] + (size_t)e * in * out;
+        const float* b = Q.b[l] + (size_t)e * out;
+        for (int j = threadIdx.x; j < out; j += blockDim.x) {
+            float acc = 0.f;
+            for (int i = 0; i < in; ++i) acc = fmaf(x[i], W[(size_t)i * out + j], acc);
+            acc += b[j];
+            if (l < Q.n_layers - 1) acc = fmaxf(acc, 0.f);
+            y[j] = acc;
+        }
+        __syncthreads();
+        float* t = x; x = y; y = t;
+    }
+    for (int j = threadIdx.x; j < Q.C; j += blockDim.x) Q.ctx[((size_t)e * Q.m + mi) * Q.C + j] = x[j];
+}
+
+cudaError_t launch_encoder(const EncoderParams& Q, cudaStream_t stream) {
+    int wmax = 0;
+    for (int l = 0; l <= Q.n_layers; ++l) wmax = max(wmax, Q.dims[l]);
+    encoder_kernel<<<dim3(Q.m, Q.E), 256, 2 * wmax * sizeof(float), stream>>>(Q);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing for the fp32 path: [E, in, out] -> zero-padded k-major image
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_f32_kernel(float* dst, const float* src, int E, int in, int out, int Kp, int Np, int col0,
+                                long long member_stride, long long layer_off, int clear) {
+    const long long total = (long long)E * Kp * Np;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Np);
+        const int k = (int)((i / Np) % Kp);
+        const int e = (int)(i / ((long long)Np * Kp));
+        float* d = dst + e * member_stride + layer_off + (long long)k * Np + c;
+        const int cs = c - col0;
+        if (cs >= 0 && cs < out && k < in) *d = src[((size_t)e * in + k) * out + cs];
+        else if (clear) *d = 0.f;
+    }
+}
+
+cudaError_t launch_pack_f32(float* dst, const float* src, int E, int in, int out, int Kp, int Np, int col0,
+                            long long member_stride, long long layer_off, int clear, cudaStream_t stream) {
+    const long long total = (long long)E * Kp * Np;
+    pack_f32_kernel<<<(int)min((total + 255) / 256, (long long)1184), 256, 0, stream>>>(dst, src, E, in, out, Kp, Np, col0,
+                                                                                        member_stride, layer_off, clear);
+    return cudaGetLastError();
+}
+
+__global__ void pack_bias_kernel(float* dst, const float* src, int E, int out, int col0, long long bias_stride, long long off) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E * out) return;
+    const int e = i / out, c = i - e * out;
+    dst[e * bias_stride + off + col0 + c] = src[(size_t)e * out + c];
+}
+
+cudaError_t launch_pack_bias(float* dst, const float* src, int E, int out, int col0, long long bias_stride, long long off,
+                             cudaStream_t stream) {
+    pack_bias_kernel<<<(E * out + 255) / 256, 256, 0, stream>>>(dst, src, E, out, col0, bias_stride, off);
+    return cudaGetLastError();
+}
+
+}  // namespace cadm

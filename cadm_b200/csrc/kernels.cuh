@@ -1,0 +1,63 @@
+// Parameter blocks and launchers of the engine's kernels (definitions in cem_kernels.cu / rollout_*.cu).
+#pragma once
+#include "common.cuh"
+
+namespace cadm {
+
+struct SampleParams {
+    int m, n_local, n_global, n_offset, hA, A;
+    int it;
+    int mode;                 // 0: CEM truncated normal, 1: uniform(-1,1), 2: discrete uniform ints (hA = h)
+    unsigned long long seed;
+    const float* mean;        // [m, hA]
+    const float* var;         // [m, hA]
+    const float* z;           // nullable, [m, n_global, hA] of this iteration (CEM) / [m, n_local, hA] explicit u (RS)
+    const int* u_int;         // nullable, RS discrete explicit draws [m, n_local, h]
+    float* actions;           // [m, n_local, hA]
+    int* actions_int;         // [m, n_local, h]
+};
+
+struct RefitParams {
+    int m, n_local, n_global, n_offset, world;
+    int h, A, k_elites, it;
+    int npad;                       // power of two >= n_global
+    float alpha;
+    unsigned long long seed;
+    const float* returns_buf;       // [world, m, n_local]
+    const float* actions;           // this rank's candidates [m, n_local, hA]
+    const float* z;                 // nullable: injected draws of this iteration [m, n_global, hA]
+    float* mean;                    // [m, hA] in/out
+    float* var;                     // [m, hA] in/out
+    float* returns_log;             // nullable, [m, n_global] slot of this iteration
+    int* elites_log;                // nullable, [m, k] slot of this iteration
+    // random shooting (mode_rs): argmax only
+    int mode_rs;
+    int* best;                      // [m]
+};
+
+struct EncoderParams {
+    int m, E, D, A, K, C;
+    int n_layers;                   // hidden + output
+    int dims[6];                    // in, h0, h1, h2, C
+    const float* W[5];              // [E, in, out]
+    const float* b[5];              // [E, 1, out]
+    const float* cp_obs;            // [m, D*K]
+    const float* cp_act;            // [m, A*K]
+    const float* cpo_mean; const float* cpo_std;   // [D*K]
+    const float* cpa_mean; const float* cpa_std;   // [A*K]
+    float* ctx;                     // [E, m, C]
+};
+
+cudaError_t launch_sample_actions(const SampleParams& S, cudaStream_t stream);
+cudaError_t launch_particle_mean(const float* ret_p, float* out, int count, int p, cudaStream_t stream);
+cudaError_t launch_refit(const RefitParams& R, cudaStream_t stream);
+cudaError_t launch_rs_gather(const float* actions, const int* actions_int, const int* best, int m, int n_local, int h,
+                             int A, float* action, int* action_int, cudaStream_t stream);
+cudaError_t launch_encoder(const EncoderParams& Q, cudaStream_t stream);
+cudaError_t launch_pack_f32(float* dst, const float* src, int E, int in, int out, int Kp, int Np, int col0,
+                            long long member_stride, long long layer_off, int clear, cudaStream_t stream);
+cudaError_t launch_pack_bias(float* dst, const float* src, int E, int out, int col0, long long bias_stride, long long off,
+                             cudaStream_t stream);
+cudaError_t launch_rollout_f32(RolloutParams P, int num_sms, cudaStream_t stream, const char** name);
+
+}  // namespace cadm

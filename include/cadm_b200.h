@@ -1,0 +1,191 @@
+/*
+ * cadm_b200.h -- C ABI of the B200-native CEM/MPC planning engine.
+ *
+ * This is the drop-in boundary for ONE hot path of younggyoseo/CaDM: the per-decision rollout of
+ * n_candidates x n_particles action sequences through the probabilistic-ensemble dynamics MLP (and the
+ * CaDM context encoder) over the planning horizon.  In the reference that path is a TensorFlow 1.15
+ * graph behind `compile_function` (cadm/utils/tensor_utils.py:6-11: sess.run(outputs, feed_dict)); the
+ * entry points below are what a binding for that boundary needs.  Each one cites what it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - All `const float*` / `float*` / `int32_t*` arguments are DEVICE pointers unless the name ends in
+ *     `_host`.  The caller owns every buffer it passes; the engine copies what it keeps.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are asynchronous with
+ *     respect to the host unless stated otherwise.
+ *   - Return value: 0 on success, negative CADM_ERR_* otherwise; cadm_last_error() gives the text.
+ *   - A handle is bound to the CUDA device that was current at cadm_plan_create() and is not thread-safe.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with CADM_ERR_CUDA.
+ *
+ * Tensor layouts are row-major with the index order written in brackets.
+ *   E ensemble members, p particles, n candidates (global), n_local = n / world candidates of this rank,
+ *   m environments planned at once, h horizon, D obs dim, P processed-obs dim, A action dim, C context
+ *   dim, K history length, k elites.
+ */
+#ifndef CADM_B200_H
+#define CADM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CADM_ABI_VERSION 1
+
+/* environment closures baked into the rollout epilogue (obs_preproc / obs_postproc / tf_reward_fn) */
+#define CADM_ENV_HALFCHEETAH   0  /* cadm/envs/half_cheetah_env.py:46-56,82-88 (also half_cheetah_cripple_env.py:60-96) */
+#define CADM_ENV_ANT           1  /* cadm/envs/ant_env.py:52-59,89-98 */
+#define CADM_ENV_SLIM_HUMANOID 2  /* cadm/envs/slim_humanoid_env.py:39-46,95-111 */
+#define CADM_ENV_CARTPOLE      3  /* cadm/envs/classic_control.py:94-101,154-166 (discrete actions) */
+#define CADM_ENV_PENDULUM      4  /* cadm/envs/classic_control.py:209-218,284-291 */
+
+/* arithmetic of the MLP contractions */
+#define CADM_PREC_FP32   0  /* fp32 FFMA: the exact-fp32 path */
+#define CADM_PREC_TC_3X  1  /* tcgen05 tensor cores, split-fp16 x3 (fp32-class accuracy) */
+#define CADM_PREC_TC_1X  2  /* tcgen05 tensor cores, single bf16 pass (fast; does NOT meet the 1e-4 bar) */
+
+/* how a particle is paired with a context-encoder member */
+#define CADM_CTX_REFERENCE 0  /* reproduce cadm/dynamics/core/utils.py:433-439 exactly (quirks Q2, Q3) */
+#define CADM_CTX_MATCHED   1  /* dynamics member e sees encoder member e (what training does, utils.py:377) */
+
+#define CADM_OK            0
+#define CADM_ERR_ARG      -1
+#define CADM_ERR_CUDA     -2
+#define CADM_ERR_STATE    -3
+#define CADM_ERR_UNSUPPORTED -4
+
+/* Mirrors the constructor arguments of MLPEnsembleCEMDynamicsModel
+ * (cadm/dynamics/mlp_cadm_ensemble_cem_dynamics.py:26-54) plus the CEM constants the reference hard-codes
+ * (cadm/dynamics/core/utils.py:111-116). */
+typedef struct CadmConfig {
+    int32_t struct_size;     /* sizeof(CadmConfig), for ABI checking */
+    int32_t env_id;          /* CADM_ENV_* */
+    int32_t obs_dim;         /* D */
+    int32_t proc_obs_dim;    /* P */
+    int32_t act_dim;         /* A */
+    int32_t ctx_dim;         /* C; 0 = no context encoder (PE-TS / vanilla) */
+    int32_t hist_len;        /* K (ignored when ctx_dim == 0) */
+    int32_t hidden;          /* width of the hidden layers (reference: 200) */
+    int32_t n_hidden;        /* number of hidden layers (reference: 4) */
+    int32_t enc_hidden[3];   /* context encoder hidden widths (reference: 256,128,64) */
+    int32_t ensemble;        /* E */
+    int32_t particles;       /* p, multiple of E */
+    int32_t candidates;      /* n (global) */
+    int32_t horizon;         /* h */
+    int32_t m_max;           /* largest number of environments planned in one call */
+    int32_t deterministic;   /* 1: delta = mean (vanilla DM), 0: PE-TS sampling */
+    int32_t discrete;        /* 1: discrete actions (random shooting only; one-hot input) */
+    int32_t num_elites;      /* reference: 50 */
+    int32_t cem_iters;       /* reference: 5 */
+    float   alpha;           /* reference: 0.1 */
+    int32_t precision;       /* CADM_PREC_* */
+    int32_t rank;            /* candidate shard of this process */
+    int32_t world;           /* number of shards; candidates % world == 0 */
+    int32_t context_layout;  /* CADM_CTX_* */
+    float   max_torque;      /* pendulum only (classic_control.py:213); 0 -> 2.0 */
+} CadmConfig;
+
+int         cadm_abi_version(void);
+/* text of the last error on this handle (handle == NULL: last error of cadm_plan_create) */
+const char* cadm_last_error(const void* handle);
+
+/* Builds the engine: replaces the graph construction in MLPEnsembleCEMDynamicsModel.__init__
+ * (mlp_ensemble_cem_dynamics.py:86-189 / mlp_cadm_ensemble_cem_dynamics.py:107-342). */
+int cadm_plan_create(const CadmConfig* cfg, void** handle);
+int cadm_plan_destroy(void* handle);
+
+/* Dynamics-MLP variables.  W[l] is [E, in_l, out_l], b[l] is [E, 1, out_l] (create_dense_layer,
+ * core/utils.py:635-647); l = 0..n_hidden-1 hidden layers, then output_mu, then output_logvar
+ * (n_layers = n_hidden + 2); max_logvar / min_logvar are [D] (core/utils.py:70-71).
+ * Replaces the variable assignment of load() (mlp_ensemble_cem_dynamics.py:333-342); call again after fit(). */
+int cadm_plan_set_weights(void* handle, const float* const* W, const float* const* b, int32_t n_layers,
+                          const float* max_logvar, const float* min_logvar, void* stream);
+
+/* Context-encoder variables cp_hidden_0..2, cp_output (core/utils.py:594-612): W[l] [E, in, out], b[l] [E, 1, out]. */
+int cadm_plan_set_encoder(void* handle, const float* const* W, const float* const* b, int32_t n_layers, void* stream);
+
+/* The normalisation placeholders of get_action (mlp_cadm_ensemble_cem_dynamics.py:345-356):
+ * obs [P], act [A], delta [D], cp_obs [D*K], cp_act [A*K]; the cp_* pointers may be NULL when ctx_dim == 0. */
+int cadm_plan_set_norm(void* handle,
+                       const float* obs_mean, const float* obs_std,
+                       const float* act_mean, const float* act_std,
+                       const float* delta_mean, const float* delta_std,
+                       const float* cp_obs_mean, const float* cp_obs_std,
+                       const float* cp_act_mean, const float* cp_act_std, void* stream);
+
+/* _get_context_pred (mlp_cadm_ensemble_cem_dynamics.py:337-342,369-380):
+ * cp_obs [m, D*K], cp_act [m, A*K] -> ctx [E, m, C]. */
+int cadm_encode_context(void* handle, int32_t m, const float* cp_obs, const float* cp_act, float* ctx, void* stream);
+
+/* One model step in the training-graph layout -- the reference's compiled `_get_pred`
+ * (mlp_ensemble_cem_dynamics.py:185-189) plus the sampled next state.
+ * obs [E, B, D], act [E, B, A] (discrete: one-hot), ctx [E, B, C] or NULL, eps [E, B, D] or NULL (NULL and not
+ * deterministic: Philox stream EPS of `seed`, row id e*B+b) -> next_obs, mu, logvar [E, B, D] (any may be NULL). */
+int cadm_predict(void* handle, int32_t B, const float* obs, const float* act, const float* ctx,
+                 const float* eps, uint64_t seed, float* next_obs, float* mu, float* logvar, void* stream);
+
+/* The horizon loop alone (core/utils.py:137-168 / 431-472) for explicit action sequences.
+ * obs [m, D], actions [m, n_local, h, A], ctx_raw [E, m, C] or NULL, eps [h, E, R, D] or NULL with
+ * R = (p/E) m n and the reference row order (NULL: Philox), `it` selects the context pairing of CEM iteration it
+ * -> particle_returns [m, n_local, p], states [h, m, n_local, p, D] or NULL (state after each step). */
+int cadm_rollout(void* handle, int32_t m, int32_t it, const float* obs, const float* actions, const float* ctx_raw,
+                 const float* eps, uint64_t seed, float* particle_returns, float* states, void* stream);
+
+/* ---- one CEM decision, phase by phase (the multi-rank form; the host all-gathers between phases) ---- */
+
+/* Start a decision: stores obs [m, D], init_mean / init_var [m, h, A] and runs the context encoder on
+ * cp_obs [m, D*K], cp_act [m, A*K] (NULL when ctx_dim == 0).  core/utils.py:121-128, 400-407. */
+int cadm_cem_begin(void* handle, int32_t m, const float* obs, const float* cp_obs, const float* cp_act,
+                   const float* init_mean, const float* init_var, void* stream);
+
+/* CEM iteration `it`: sample this rank's candidates (core/utils.py:131-135), roll them out (:137-168) and
+ * average over particles (:170) into this rank's slice of the returns buffer.
+ * z [iters, m, n, h, A] or NULL (NULL: Philox stream Z of `seed`); eps [iters, h, E, R, D] or NULL. */
+int cadm_cem_rollout(void* handle, int32_t it, uint64_t seed, const float* z, const float* eps, void* stream);
+
+/* Device buffer [world, m, n_local] of candidate returns; rank r writes slice r.  With world > 1 the host
+ * all-gathers it in place between cadm_cem_rollout and cadm_cem_refit (ncclAllGather, one per iteration). */
+float* cadm_cem_returns_buffer(void* handle);
+int64_t cadm_cem_returns_slice_elems(void* handle);   /* m * n_local of the decision in flight */
+
+/* top_k + gather + refit + EMA (core/utils.py:171-182) from the gathered returns buffer. */
+int cadm_cem_refit(void* handle, int32_t it, void* stream);
+
+/* Results of the decision: mean / var [m, h, A] (mean is the UNCLIPPED optimal_action_var, core/utils.py:184),
+ * returns [iters, m, n], elites [iters, m, k] int32 (global candidate ids).  Any pointer may be NULL. */
+int cadm_cem_finish(void* handle, float* mean, float* var, float* returns, int32_t* elites, void* stream);
+
+/* The whole decision for world == 1: begin + iters x (rollout, refit) + finish.  This is `_get_cem_action`
+ * (mlp_ensemble_cem_dynamics.py:173-178 / mlp_cadm_...:320-328). */
+int cadm_plan_cem(void* handle, int32_t m, const float* obs, const float* cp_obs, const float* cp_act,
+                  const float* init_mean, const float* init_var, uint64_t seed, const float* z, const float* eps,
+                  float* mean, float* var, float* returns, int32_t* elites, void* stream);
+
+/* Same with HOST buffers: copies the inputs to the device, runs the decision, copies `action_host`
+ * [m, h, A] = clip(mean, -1, 1) back (mlp_ensemble_cem_dynamics.py:205-206) and synchronises the stream.
+ * This is the call behind DynamicsModel.get_action(); pinned host memory makes the copies asynchronous. */
+int cadm_plan_cem_host(void* handle, int32_t m, const float* obs_host, const float* cp_obs_host,
+                       const float* cp_act_host, const float* init_mean_host, const float* init_var_host,
+                       uint64_t seed, float* action_host, void* stream);
+
+/* Random shooting, `_get_rs_action` (core/utils.py:186-246 / 490-561).  u: explicit draws, [m, n_local, h, A]
+ * uniform(-1,1) actions (continuous) or NULL (Philox); for discrete models u_int [m, n_local, h] int32 or NULL.
+ * world == 1 only.  -> action [m, A] (continuous, unclipped) or action_int [m], returns [m, n], best [m]. */
+int cadm_plan_rs(void* handle, int32_t m, const float* obs, const float* cp_obs, const float* cp_act,
+                 uint64_t seed, const float* u, const int32_t* u_int, const float* eps,
+                 float* action, int32_t* action_int, float* returns, int32_t* best, void* stream);
+
+/* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
+int64_t cadm_launch_count(void* handle);
+/* Name of the rollout kernel variant in use, e.g. "rollout_f32<32>" (for reports). */
+const char* cadm_kernel_name(void* handle);
+/* Duration in ms of the rollout kernels of the last cadm_plan_cem*, measured with CUDA events on `stream`
+ * when timing is enabled (cadm_set_timing(handle, 1)); sum over the iterations.  Synchronises. */
+int   cadm_set_timing(void* handle, int32_t on);
+float cadm_last_rollout_ms(void* handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CADM_B200_H */
