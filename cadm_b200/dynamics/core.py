@@ -33,7 +33,8 @@ class PlannerModelBase:
     def _init_common(self, name, env, hidden_sizes, hidden_nonlinearity, output_nonlinearity, normalize_input,
                      n_forwards, n_candidates, ensemble_size, n_particles, use_cem, deterministic,
                      cp_hidden_sizes=(256, 128, 64), context_out_dim=10, history_length=10, state_diff=False,
-                     seed=0, m_max=32, precision="fp32", device=None, rank=0, world=1, context_layout="reference"):
+                     seed=0, m_max=32, precision="fp32", device=None, rank=0, world=1, context_layout="reference",
+                     num_elites=50, cem_iters=5, alpha=0.1):
         if hidden_nonlinearity not in _ACTIVATIONS or output_nonlinearity not in _ACTIVATIONS:
             raise KeyError(hidden_nonlinearity)                      # the reference indexes _activations[...]
         if hidden_nonlinearity != "swish" or output_nonlinearity is not None:
@@ -95,6 +96,7 @@ class PlannerModelBase:
                             enc_hidden=tuple(self.cp_hidden_sizes), ensemble=E, particles=n_particles,
                             candidates=n_candidates, horizon=n_forwards, m_max=m_max, deterministic=deterministic,
                             discrete=self.discrete, precision=precision, rank=rank, world=world,
+                            num_elites=num_elites, cem_iters=cem_iters, alpha=alpha,
                             context_layout=context_layout, max_torque=getattr(self.env, "max_torque", 2.0))
         self.engine = PlannerEngine(cfg, device=device)
         self._push_params()

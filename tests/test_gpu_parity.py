@@ -53,7 +53,7 @@ def test_predict_one_step(config, precision):
 @pytest.mark.parametrize("config,m,n", [("C1", 1, 200), ("C2", 1, 40), ("C2", 3, 16), ("C3", 3, 16), ("C4", 2, 24)])
 def test_rollout_states_and_returns(config, m, n, precision):
     """30-step rollouts with injected noise: every intermediate state and the particle returns."""
-    model, env, cfg = _model(config, candidates=n, precision=precision)
+    model, env, cfg = _model(config, candidates=n, precision=precision, num_elites=min(50, n))
     prm, enc, norm, oenv = oracle_pack(model)
     from cadm_b200.synth import synthetic_inputs
     inp = synthetic_inputs(env, m, cfg["horizon"], cfg["context"], seed=1)
