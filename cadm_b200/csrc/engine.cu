@@ -26,6 +26,12 @@ struct Engine {
     // parameters
     float* wpack = nullptr;
     float* bpack = nullptr;
+    // tensor-core image (hi/lo split, UMMA layout) and its 16-padded biases
+    unsigned char* wimg = nullptr;
+    float* bpack_tc = nullptr;
+    int Np16 = 0, NHp16 = 0, nkb0 = 0, nkbH = 0;
+    long long wimg_member_stride = 0, bias_stride_tc = 0;
+    int precision = CADM_PREC_FP32;
     float* max_lv = nullptr;
     float* min_lv = nullptr;
     bool have_weights = false, have_encoder = false, have_norm = false;
@@ -129,12 +135,19 @@ int run_rollout(Engine* E, RolloutParams& P, cudaStream_t s) {
         E->ev_used += 2;
         CU(E, cudaEventRecord(e0, s));
     }
-    switch (E->cfg.precision) {
+    switch (E->precision) {
         case CADM_PREC_FP32:
             CU(E, launch_rollout_f32(P, E->num_sms, s, &E->kernel_name));
             break;
+        case CADM_PREC_TC_3X:
+        case CADM_PREC_TC_1X:
+            P.bpack = E->bpack_tc;
+            P.bias_stride = E->bias_stride_tc;
+            CU(E, launch_rollout_tc(P, E->wimg, E->wimg_member_stride, E->precision == CADM_PREC_TC_3X ? 3 : 1, E->num_sms, s,
+                                    &E->kernel_name));
+            break;
         default:
-            return fail(E, CADM_ERR_UNSUPPORTED, "precision mode not built into this library");
+            return fail(E, CADM_ERR_UNSUPPORTED, "unknown precision mode");
     }
     E->launches++;
     if (E->timing) CU(E, cudaEventRecord(e1, s));
@@ -190,7 +203,7 @@ int cadm_plan_create(const CadmConfig* cfg, void** handle) {
     if (c.env_id == CADM_ENV_ANT && c.proc_obs_dim != c.obs_dim - 1) return bad("ant: proc_obs_dim must be obs_dim - 1");
     if (c.env_id != CADM_ENV_ANT && c.proc_obs_dim != c.obs_dim) return bad("proc_obs_dim must equal obs_dim for this env");
     if (c.ctx_dim > 0 && c.hist_len < 1) return bad("hist_len must be positive with a context encoder");
-    if (c.precision != CADM_PREC_FP32) return bad("precision mode not built into this library");
+    if (c.precision < CADM_PREC_FP32 || c.precision > CADM_PREC_TC_1X) return bad("unknown precision mode");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -215,6 +228,13 @@ int cadm_plan_create(const CadmConfig* cfg, void** handle) {
     E->n_offset = c.rank * E->n_local;
     E->q = c.particles / c.ensemble;
     E->hA = c.horizon * c.act_dim;
+    E->precision = c.precision;
+    E->Np16 = round_up(c.hidden, 16);
+    E->NHp16 = round_up(2 * c.obs_dim, 16);
+    E->nkb0 = round_up(E->In, 16) / 16;
+    E->nkbH = E->Np16 / 16;
+    E->wimg_member_stride = ((long long)(E->nkb0 + (c.n_hidden - 1) * E->nkbH) * E->Np16 + (long long)E->nkbH * E->NHp16) * 64;
+    E->bias_stride_tc = (long long)c.n_hidden * E->Np16 + E->NHp16;
     E->member_stride = (long long)E->Kp0 * E->Hp + (long long)(c.n_hidden - 1) * E->Hp * E->Hp + (long long)E->Hp * E->NHp;
     E->bias_stride = (long long)c.n_hidden * E->Hp + E->NHp;
 
@@ -223,6 +243,8 @@ int cadm_plan_create(const CadmConfig* cfg, void** handle) {
     auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     A(dalloc(E, &E->wpack, (size_t)c.ensemble * E->member_stride));
     A(dalloc(E, &E->bpack, (size_t)c.ensemble * E->bias_stride));
+    A(dalloc(E, &E->wimg, (size_t)c.ensemble * E->wimg_member_stride));
+    A(dalloc(E, &E->bpack_tc, (size_t)c.ensemble * E->bias_stride_tc));
     A(dalloc(E, &E->max_lv, c.obs_dim));
     A(dalloc(E, &E->min_lv, c.obs_dim));
     A(dalloc(E, &E->obs_mean, c.proc_obs_dim)); A(dalloc(E, &E->obs_std, c.proc_obs_dim));
@@ -288,6 +310,24 @@ int cadm_plan_set_weights(void* handle, const float* const* W, const float* cons
     CU(E, launch_pack_bias(E->bpack, b[c.n_hidden], c.ensemble, c.obs_dim, 0, E->bias_stride, boff, s));
     CU(E, launch_pack_bias(E->bpack, b[c.n_hidden + 1], c.ensemble, c.obs_dim, c.obs_dim, E->bias_stride, boff, s));
     E->launches += 4;
+    // tensor-core image: per layer nkb K16 blocks of [hi | lo], N padded to 16
+    {
+        long long toff = 0, tboff = 0;
+        for (int l = 0; l < c.n_hidden; ++l) {
+            const int in = l == 0 ? E->In : c.hidden;
+            const int nkb = l == 0 ? E->nkb0 : E->nkbH;
+            CU(E, launch_pack_tc(E->wimg, W[l], c.ensemble, in, c.hidden, 0, nkb, E->Np16, E->wimg_member_stride, toff, 1, s));
+            CU(E, launch_pack_bias(E->bpack_tc, b[l], c.ensemble, c.hidden, 0, E->bias_stride_tc, tboff, s));
+            toff += (long long)nkb * E->Np16 * 64;
+            tboff += E->Np16;
+            E->launches += 2;
+        }
+        CU(E, launch_pack_tc(E->wimg, W[c.n_hidden], c.ensemble, c.hidden, c.obs_dim, 0, E->nkbH, E->NHp16, E->wimg_member_stride, toff, 1, s));
+        CU(E, launch_pack_tc(E->wimg, W[c.n_hidden + 1], c.ensemble, c.hidden, c.obs_dim, c.obs_dim, E->nkbH, E->NHp16, E->wimg_member_stride, toff, 0, s));
+        CU(E, launch_pack_bias(E->bpack_tc, b[c.n_hidden], c.ensemble, c.obs_dim, 0, E->bias_stride_tc, tboff, s));
+        CU(E, launch_pack_bias(E->bpack_tc, b[c.n_hidden + 1], c.ensemble, c.obs_dim, c.obs_dim, E->bias_stride_tc, tboff, s));
+        E->launches += 4;
+    }
     CU(E, cudaMemcpyAsync(E->max_lv, max_logvar, c.obs_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CU(E, cudaMemcpyAsync(E->min_lv, min_logvar, c.obs_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
     E->have_weights = true;
@@ -590,6 +630,30 @@ int cadm_plan_rs(void* handle, int32_t m, const float* obs, const float* cp_obs,
     E->launches += 3;
     if (returns) CU(E, cudaMemcpyAsync(returns, E->returns_log, (size_t)m * c.candidates * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (best) CU(E, cudaMemcpyAsync(best, E->best, (size_t)m * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    return CADM_OK;
+}
+
+int cadm_set_precision(void* handle, int32_t precision) {
+    Engine* E = H(handle);
+    if (!E) return CADM_ERR_ARG;
+    if (precision < CADM_PREC_FP32 || precision > CADM_PREC_TC_1X) return fail(E, CADM_ERR_ARG, "unknown precision mode");
+    E->precision = precision;
+    return CADM_OK;
+}
+
+int cadm_selftest_tc_gemm(const float* X, const float* W, int32_t K, int32_t N, int32_t terms, float* out, void* stream) {
+    if (!X || !W || !out || K < 1 || K > 208 || N < 16 || N > 208 || N % 16 || (terms != 1 && terms != 3))
+        return fail(nullptr, CADM_ERR_ARG, "selftest: need 1 <= K <= 208, N a multiple of 16 in 16..208, terms 1 or 3");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nkb = (K + 15) / 16;
+    unsigned char* img = nullptr;
+    cudaError_t e = cudaMalloc(&img, (size_t)nkb * N * 64);
+    if (e != cudaSuccess) return fail(nullptr, CADM_ERR_CUDA, cudaGetErrorString(e));
+    e = launch_pack_tc(img, W, 1, K, N, 0, nkb, N, (long long)nkb * N * 64, 0, 1, s);
+    if (e == cudaSuccess) e = launch_tc_gemm_selftest(X, img, K, N, terms, out, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(img);
+    if (e != cudaSuccess) return fail(nullptr, CADM_ERR_CUDA, cudaGetErrorString(e));
     return CADM_OK;
 }
 

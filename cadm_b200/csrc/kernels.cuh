@@ -59,5 +59,11 @@ cudaError_t launch_pack_f32(float* dst, const float* src, int E, int in, int out
 cudaError_t launch_pack_bias(float* dst, const float* src, int E, int out, int col0, long long bias_stride, long long off,
                              cudaStream_t stream);
 cudaError_t launch_rollout_f32(RolloutParams P, int num_sms, cudaStream_t stream, const char** name);
+cudaError_t launch_rollout_tc(RolloutParams P, const unsigned char* wimg, long long wimg_member_stride, int terms,
+                              int num_sms, cudaStream_t stream, const char** name);
+cudaError_t launch_pack_tc(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad,
+                           long long member_stride, long long layer_off, int clear, cudaStream_t stream);
+cudaError_t launch_tc_gemm_selftest(const float* X, const unsigned char* wimg, int K, int N, int terms, float* out,
+                                    cudaStream_t stream);
 
 }  // namespace cadm

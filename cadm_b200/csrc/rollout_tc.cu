@@ -1,0 +1,597 @@
+// Persistent tensor-core rollout kernel (CADM_PREC_TC_3X / CADM_PREC_TC_1X): tcgen05.mma with accumulators in TMEM.
+//
+// One CTA per SM; a CTA owns a tile of up to 128 rows (TMEM lanes) of ONE ensemble member and carries it through all
+// h horizon steps of a CEM iteration -- state, return accumulator, activations and accumulators never leave the SM.
+// Every layer is D[128 x N] = X[128 x K] * W^T[N x K] on the 5th-gen tensor cores (M = 128, N = 208 / 2D padded, K = 16
+// per instruction, kind::f16, fp32 accumulate in TMEM).
+//
+// Precision (CADM_PREC_TC_3X): every fp32 operand is split as x = hi + lo, hi = fp16(x), lo = bf16(x - hi)
+// (19-20 significant bits, bf16 exponent range for the residual) and a product is 3 MMAs into ONE accumulator:
+//     X_hi * W_hi (f16 x f16)  +  X_hi * W_lo (f16 x bf16)  +  X_lo * W_hi (bf16 x f16)
+// (the A and B formats are separate fields of the instruction descriptor, so mixed f16/bf16 MMAs are legal).  The
+// dropped lo*lo term and the bf16 rounding of lo are ~2^-20 relative -- fp32-class for the 1e-4 parity bar.
+// CADM_PREC_TC_1X issues only the first MMA (fp16 operands; fast, does not claim the bar).
+//
+// Warp roles (320 threads):
+//   warp 0      weight producer: streams the member's packed weight image from L2 through a shared-memory ring with
+//               1-D bulk async copies (TMA engine, mbarrier complete_tx), one stage = one K16 block (hi + lo)
+//   warp 1      MMA issuer (one elected lane): waits "activation block ready" + "weight stage full", issues the MMAs,
+//               tcgen05.commit frees the weight stage / publishes the accumulator
+//   warps 2-9   epilogue: TMEM -> registers (tcgen05.ld, lane = row) -> bias + swish -> hi/lo split -> shared memory in
+//               the UMMA K-major layout -> "block ready".  Two warps per TMEM lane quarter split the columns.  The next
+//               layer's MMAs start per K16 block while the epilogue is still producing later blocks, and two TMEM
+//               accumulators alternate, so the tensor pipe and the epilogue overlap inside one dependent chain.
+//   The same warps run the per-step prologue (obs_preproc + normalise + concat, reward) and the final epilogue
+//   (denormalise, bounded logvar, Gaussian sample, obs_postproc) -- core/utils.py:141-168 fused as in rollout_f32.cu.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include "rng.cuh"
+
+namespace cadm {
+
+constexpr int kTcThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kTileRows = 128;
+constexpr int kMaxKB = 13;                     // K16 blocks of the widest layer (208 / 16)
+constexpr int kXChunkBytes = 2048;             // one 8-wide k-chunk of all 128 rows: 128 rows x 16 B
+constexpr int kXBytes = 2 * kMaxKB * kXChunkBytes;   // 53248 per operand half (hi or lo)
+constexpr int kMaxStageBytes = 2 * 208 * 32;   // hi + lo block of one K16 step, N = 208
+
+struct TcSmem {
+    size_t off_xhi, off_xlo, off_w, off_s, off_bias, off_vec, off_rowi, off_bar, total;
+    int stages;
+};
+
+__host__ __device__ inline TcSmem tc_smem_layout(int D, int n_hidden, int Np, int NHp, int stages) {
+    TcSmem L;
+    size_t o = 0;
+    L.off_xhi = o; o += kXBytes;
+    L.off_xlo = o; o += kXBytes;
+    L.off_w = o; o += (size_t)stages * kMaxStageBytes;
+    L.off_s = o; o += (size_t)round_up(kTileRows * (D + 1), 4) * 4;
+    L.off_bias = o; o += (size_t)round_up(n_hidden * Np + NHp, 4) * 4;
+    L.off_vec = o; o += (size_t)(2 * kMaxObs + 2 * kMaxAct + 5 * kMaxObs) * 4;
+    L.off_rowi = o; o += (size_t)kTileRows * 6 * 4;
+    o = (o + 15) / 16 * 16;
+    L.off_bar = o; o += (size_t)(2 * 8 + kMaxKB + 2 + 2) * 8;     // w_full[8], w_empty[8], x_ready[13], acc_full[2], tmem slot
+    L.total = o;
+    L.stages = stages;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: [E, in, out] fp32 -> per member, per K16 block: [hi block | lo block], each N x 16 in the UMMA
+// K-major no-swizzle layout: byte(n, kk) = (kk / 8) * (16 N) + 16 n + 2 (kk % 8)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_tc_kernel(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad,
+                               long long member_stride, long long layer_off, int clear) {
+    const long long per_member = (long long)nkb * Npad * 16;
+    const long long total = (long long)E * per_member;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i / per_member);
+        long long r = i - (long long)e * per_member;
+        const int kb = (int)(r / (Npad * 16));
+        r -= (long long)kb * Npad * 16;
+        const int n = (int)(r / 16), kk = (int)(r % 16);
+        const int k = kb * 16 + kk;
+        const int ns = n - col0;
+        const bool valid = ns >= 0 && ns < out && k < in;
+        if (!valid && !clear) continue;
+        const float w = valid ? src[((size_t)e * in + k) * out + ns] : 0.f;
+        uint32_t hi, lo;
+        tc::split2(w, 0.f, hi, lo);
+        unsigned char* blk = dst + e * member_stride + layer_off + (long long)kb * (2 * Npad * 32);
+        const int off = (kk >> 3) * (16 * Npad) + 16 * n + 2 * (kk & 7);
+        *reinterpret_cast<unsigned short*>(blk + off) = (unsigned short)(hi & 0xffffu);
+        *reinterpret_cast<unsigned short*>(blk + Npad * 32 + off) = (unsigned short)(lo & 0xffffu);
+    }
+}
+
+cudaError_t launch_pack_tc(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad,
+                           long long member_stride, long long layer_off, int clear, cudaStream_t stream) {
+    const long long total = (long long)E * nkb * Npad * 16;
+    pack_tc_kernel<<<(int)min((total + 255) / 256, (long long)2368), 256, 0, stream>>>(dst, src, E, in, out, col0, nkb, Npad,
+                                                                                       member_stride, layer_off, clear);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Ring {
+    int stage;
+    uint32_t phase;
+    int n;
+    __device__ __forceinline__ void advance() {
+        if (++stage == n) { stage = 0; phase ^= 1u; }
+    }
+};
+
+// store 16 consecutive features (one K16 block `kb`) of row `row` as hi / lo halves in the UMMA A layout
+__device__ __forceinline__ void store_block16(unsigned char* xhi, unsigned char* xlo, int kb, int row, const float (&y)[16]) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tc::split2(y[2 * j], y[2 * j + 1], h[j], l[j]);
+    const int o0 = (2 * kb) * kXChunkBytes + row * 16;
+    const int o1 = o0 + kXChunkBytes;
+    *reinterpret_cast<uint4*>(xhi + o0) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(xhi + o1) = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4*>(xlo + o0) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(xlo + o1) = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+// publish a finished activation block to the MMA warp (generic-proxy writes -> async-proxy reads)
+__device__ __forceinline__ void publish_block(uint64_t* bar, int lane) {
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(bar);
+}
+
+struct TcParams {
+    RolloutParams R;
+    const unsigned char* wimg;   // packed tensor-core weight image
+    long long wimg_member_stride;
+    int Np;                      // hidden width padded to 16 (N of the hidden layers, K of layers >= 1)
+    int NHp;                     // 2D padded to 16
+    int nkb0;                    // K16 blocks of layer 0
+    int nkbH;                    // K16 blocks of the other layers
+    int terms;                   // 3 (hi/lo split) or 1
+    int stages;
+    int tiles_per_member, total_tiles;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_constant__ TcParams T) {
+    const RolloutParams& P = T.R;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const TcSmem L = tc_smem_layout(P.D, P.n_hidden, T.Np, T.NHp, T.stages);
+    unsigned char* xhi = smem + L.off_xhi;
+    unsigned char* xlo = smem + L.off_xlo;
+    unsigned char* wring = smem + L.off_w;
+    float* S = reinterpret_cast<float*>(smem + L.off_s);
+    float* bias = reinterpret_cast<float*>(smem + L.off_bias);
+    float* vec = reinterpret_cast<float*>(smem + L.off_vec);
+    int* rowi = reinterpret_cast<int*>(smem + L.off_rowi);
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    uint64_t* w_empty = w_full + 8;
+    uint64_t* x_ready = w_empty + 8;
+    uint64_t* acc_full = x_ready + kMaxKB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+
+    float* v_obs_mean = vec;
+    float* v_obs_den = vec + kMaxObs;
+    float* v_act_mean = vec + 2 * kMaxObs;
+    float* v_act_den = v_act_mean + kMaxAct;
+    float* v_dmean = v_act_den + kMaxAct;
+    float* v_dscale = v_dmean + kMaxObs;
+    float* v_2logstd = v_dscale + kMaxObs;
+    float* v_maxlv = v_2logstd + kMaxObs;
+    float* v_minlv = v_maxlv + kMaxObs;
+    int* r_mi = rowi;
+    int* r_src = rowi + kTileRows;
+    int* r_pi = rowi + 2 * kTileRows;
+    int* r_ctx = rowi + 3 * kTileRows;
+    int* r_rid = rowi + 4 * kTileRows;
+    int* r_eps = rowi + 5 * kTileRows;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nstage = T.stages;
+    const int gemms_per_step = P.n_hidden + 1;
+    const int kb_split = T.nkbH / 2;               // epilogue group A: blocks [0, kb_split), group B: the rest
+
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
+        for (int k = 0; k < kMaxKB; ++k) ptx::mbar_init(&x_ready[k], 4);
+        ptx::mbar_init(&acc_full[0], 1);
+        ptx::mbar_init(&acc_full[1], 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, 512);
+        tc::tmem_relinquish();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t stage_bytes_h = 2u * T.Np * 32u;      // hi + lo of a hidden K16 block
+    const uint32_t stage_bytes_o = 2u * T.NHp * 32u;     // heads
+
+    // ======================= warp 0: weight producer =============================================
+    if (warp == 0) {
+        if (lane == 0) {
+            Ring rp{0, 0, nstage};
+            for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
+                const int e = tile / T.tiles_per_member;
+                const unsigned char* wsrc = T.wimg + (size_t)e * T.wimg_member_stride;
+                for (int t = 0; t < P.h; ++t) {
+                    size_t off = 0;
+                    for (int g = 0; g < gemms_per_step; ++g) {
+                        const int nkb = g == 0 ? T.nkb0 : T.nkbH;
+                        const uint32_t bytes = g == P.n_hidden ? stage_bytes_o : stage_bytes_h;
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            ptx::mbar_wait(&w_empty[rp.stage], rp.phase ^ 1u);
+                            ptx::mbar_arrive_expect_tx(&w_full[rp.stage], bytes);
+                            ptx::bulk_g2s(wring + (size_t)rp.stage * kMaxStageBytes, wsrc + off, bytes, &w_full[rp.stage]);
+                            off += bytes;
+                            rp.advance();
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ======================= warp 1: MMA issuer ==================================================
+    else if (warp == 1) {
+        if (lane == 0) {
+            Ring rc{0, 0, nstage};
+            uint32_t xphase = 0;          // bit kb = parity to wait for on x_ready[kb]
+            uint32_t g_count = 0;         // running GEMM index: accumulator buffer = g & 1
+            const uint32_t xhi_a = ptx::smem_u32(xhi), xlo_a = ptx::smem_u32(xlo), w_a = ptx::smem_u32(wring);
+            for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
+                for (int t = 0; t < P.h; ++t) {
+                    for (int g = 0; g < gemms_per_step; ++g) {
+                        const int nkb = g == 0 ? T.nkb0 : T.nkbH;
+                        const uint32_t N = g == P.n_hidden ? (uint32_t)T.NHp : (uint32_t)T.Np;
+                        const uint32_t d_tmem = tmem_base + (g_count & 1u) * 256u;
+                        const uint32_t id_hh = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
+                        const uint32_t id_hl = tc::idesc_f16(tc::kFmtF16, tc::kFmtBF16, N);
+                        const uint32_t id_lh = tc::idesc_f16(tc::kFmtBF16, tc::kFmtF16, N);
+                        for (int kb = 0; kb < nkb; ++kb) {
+                            ptx::mbar_wait(&x_ready[kb], (xphase >> kb) & 1u);
+                            xphase ^= 1u << kb;
+                            ptx::mbar_wait(&w_full[rc.stage], rc.phase);
+                            tc::fence_after_sync();
+                            const uint32_t wb = w_a + rc.stage * kMaxStageBytes;
+                            const uint64_t a_hi = tc::smem_desc(xhi_a + 2 * kb * kXChunkBytes, kXChunkBytes, 128);
+                            const uint64_t a_lo = tc::smem_desc(xlo_a + 2 * kb * kXChunkBytes, kXChunkBytes, 128);
+                            const uint64_t b_hi = tc::smem_desc(wb, 16 * N, 128);
+                            const uint64_t b_lo = tc::smem_desc(wb + N * 32, 16 * N, 128);
+                            tc::mma_f16_ss(d_tmem, a_hi, b_hi, id_hh, kb > 0 ? 1u : 0u);
+                            if (T.terms == 3) {
+                                tc::mma_f16_ss(d_tmem, a_hi, b_lo, id_hl, 1u);
+                                tc::mma_f16_ss(d_tmem, a_lo, b_hi, id_lh, 1u);
+                            }
+                            tc::mma_commit(&w_empty[rc.stage]);
+                            rc.advance();
+                        }
+                        tc::mma_commit(&acc_full[g_count & 1u]);
+                        ++g_count;
+                    }
+                }
+            }
+        }
+    }
+    // ======================= warps 2..9: prologue / epilogue ======================================
+    else {
+        const int et = tid - 64;                       // 0..255
+        const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+        const int group = (warp - 2) >> 2;             // 0: blocks [0, kb_split), 1: the rest
+        const int row = quarter * 32 + lane;           // tile row == TMEM lane
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint32_t g_count = 0;
+        const int D = P.D, A = P.A;
+        const size_t eps_step_stride = (size_t)P.E * P.q * P.m * P.n_global * D;
+
+        // one-time: normalisation vectors
+        for (int i = et; i < P.P; i += kEpiThreads) { v_obs_mean[i] = P.obs_mean[i]; v_obs_den[i] = P.obs_std[i] + 1e-10f; }
+        for (int i = et; i < A; i += kEpiThreads) { v_act_mean[i] = P.act_mean[i]; v_act_den[i] = P.act_std[i] + 1e-10f; }
+        for (int i = et; i < D; i += kEpiThreads) {
+            v_dmean[i] = P.delta_mean[i];
+            v_dscale[i] = P.delta_std[i] + 1e-10f;
+            v_2logstd[i] = 2.0f * logf(P.delta_std[i]);
+            v_maxlv[i] = P.max_lv[i];
+            v_minlv[i] = P.min_lv[i];
+        }
+
+        for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
+            const int e = tile / T.tiles_per_member;
+            const int tile_row0 = (tile - e * T.tiles_per_member) * P.rows_per_cta;
+            const int nrows = min(P.rows_per_cta, P.rows_per_member - tile_row0);
+            ptx::bar_sync(1, kEpiThreads);             // previous tile fully retired before its smem is reused
+            for (int i = et; i < P.n_hidden * T.Np + T.NHp; i += kEpiThreads) bias[i] = P.bpack[(size_t)e * P.bias_stride + i];
+            if (et < kTileRows) {
+                const int r = et;
+                int mi = 0, src = 0, pi = 0, cidx = 0, rid = 0, er = 0;
+                if (r < nrows) {
+                    const int rl = tile_row0 + r;
+                    if (P.row_mode == kRowsPlanner) {
+                        int nl;
+                        planner_row(P, e, rl, mi, nl, pi);
+                        src = mi * P.n_local + nl;
+                        const int ng = P.n_offset + nl;
+                        rid = (mi * P.n_global + ng) * P.p + pi;
+                        cidx = P.ctx_mode ? planner_ctx_index(P, e, mi, pi) : 0;
+                        const int jq = pi - e * P.q;
+                        er = e * (P.q * P.m * P.n_global) + (jq * P.m + mi) * P.n_global + ng;
+                    } else {
+                        src = e * P.rows_per_member + rl;
+                        rid = src; cidx = src; er = src;
+                    }
+                }
+                r_mi[r] = mi; r_src[r] = src; r_pi[r] = pi; r_ctx[r] = cidx; r_rid[r] = rid; r_eps[r] = er;
+            }
+            ptx::bar_sync(1, kEpiThreads);
+            for (int i = et; i < kTileRows * D; i += kEpiThreads) {
+                const int r = i / D, d = i - r * D;
+                float v = 0.f;
+                if (r < nrows) v = (P.row_mode == kRowsPlanner) ? P.obs0[r_mi[r] * D + d] : P.obs0[(size_t)r_src[r] * D + d];
+                S[r * (D + 1) + d] = v;
+            }
+            ptx::bar_sync(1, kEpiThreads);
+
+            float ret = 0.f;
+            const bool valid = row < nrows;
+#pragma unroll 1
+            for (int t = 0; t < P.h; ++t) {
+                // ---------- prologue: reward of the current state; layer-0 input blocks -----------------
+                const float* s = S + row * (D + 1);
+                if (group == 0 && valid) {
+                    if (env_reward_reads_next(P.env_id)) {
+                        if (t > 0) ret += env_reward_next(P.env_id, s);
+                    } else {
+                        float a[kMaxAct];
+                        const float* ap = P.actions + ((size_t)r_src[row] * P.h + t) * A;
+#pragma unroll 1
+                        for (int i = 0; i < A; ++i) a[i] = __ldg(ap + i);
+                        ret += env_reward_current(P.env_id, s, a, A, P.max_torque);
+                    }
+                }
+                for (int kb = group; kb < T.nkb0; kb += 2) {      // layer 0: the two groups alternate blocks
+                    float y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = kb * 16 + j;
+                        float v = 0.f;
+                        if (valid && k < P.In) {
+                            if (k < P.P) {
+                                v = __fdiv_rn(env_preproc(P.env_id, s, k) - v_obs_mean[k], v_obs_den[k]);
+                            } else if (k < P.P + A) {
+                                const int ai = k - P.P;
+                                if (P.discrete) {
+                                    if (P.row_mode == kRowsPlanner) v = __ldg(P.actions_int + (size_t)r_src[row] * P.h + t) == ai ? 1.f : 0.f;
+                                    else v = __ldg(P.actions + (size_t)r_src[row] * A + ai);
+                                } else {
+                                    const float av = __ldg(P.actions + ((size_t)r_src[row] * P.h + t) * A + ai);
+                                    v = __fdiv_rn(av - v_act_mean[ai], v_act_den[ai]);
+                                }
+                            } else {
+                                v = __ldg(P.ctx + (size_t)r_ctx[row] * P.C + (k - P.P - A));
+                            }
+                        }
+                        y[j] = v;
+                    }
+                    store_block16(xhi, xlo, kb, row, y);
+                    publish_block(&x_ready[kb], lane);
+                }
+
+                // ---------- hidden layers: accumulator -> bias + swish -> next layer's A operand ---------
+#pragma unroll 1
+                for (int l = 0; l < P.n_hidden; ++l) {
+                    const uint32_t buf = g_count & 1u;
+                    ptx::mbar_wait(&acc_full[buf], (g_count >> 1) & 1u);
+                    tc::fence_after_sync();
+                    ++g_count;
+                    const uint32_t tcol = tmem_lane + buf * 256u;
+                    const float* bl = bias + l * T.Np;
+                    const int kb0 = group == 0 ? 0 : kb_split, kb1 = group == 0 ? kb_split : T.nkbH;
+                    uint32_t v[16];
+                    tc::tmem_ld16(tcol + kb0 * 16, v);
+#pragma unroll 1
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        tc::tmem_wait_ld();
+                        float y[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
+                        if (kb + 1 < kb1) tc::tmem_ld16(tcol + (kb + 1) * 16, v);      // prefetch the next block
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) y[j] = tc::swish_fast(y[j] + bl[kb * 16 + j]);
+                        store_block16(xhi, xlo, kb, row, y);
+                        tc::fence_before_sync();
+                        publish_block(&x_ready[kb], lane);
+                    }
+                }
+
+                // ---------- heads -> Hd (aliases X_hi once the head GEMM has completed) ------------------
+                {
+                    const uint32_t buf = g_count & 1u;
+                    ptx::mbar_wait(&acc_full[buf], (g_count >> 1) & 1u);
+                    tc::fence_after_sync();
+                    ++g_count;
+                    float* Hd = reinterpret_cast<float*>(xhi);       // [NHp][128]  (column-major: conflict-free)
+                    const uint32_t tcol = tmem_lane + buf * 256u;
+                    const float* bl = bias + P.n_hidden * T.Np;
+                    const int nb8 = T.NHp / 8;
+                    for (int b = group; b < nb8; b += 2) {
+                        uint32_t v[8];
+                        tc::tmem_ld8(tcol + b * 8, v);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) Hd[(b * 8 + j) * kTileRows + row] = __uint_as_float(v[j]) + bl[b * 8 + j];
+                    }
+                    tc::fence_before_sync();
+                }
+                ptx::bar_sync(1, kEpiThreads);
+
+                // ---------- final epilogue: sample, next state ------------------------------------------
+                {
+                    const float* Hd = reinterpret_cast<const float*>(xhi);
+                    const int nblk = (D + 3) / 4;
+                    for (int item = et; item < kTileRows * nblk; item += kEpiThreads) {
+                        const int j = item / kTileRows, r = item - j * kTileRows;
+                        if (r >= nrows) continue;
+                        float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (!P.deterministic) {
+                            if (P.eps != nullptr) {
+                                const float* ep = P.eps + (P.row_mode == kRowsPlanner ? (size_t)t * eps_step_stride : 0) +
+                                                  (size_t)r_eps[r] * D + 4 * j;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    if (4 * j + i < D) nz[i] = __ldg(ep + i);
+                            } else {
+                                normal4(P.seed, (uint32_t)j, (uint32_t)r_rid[r], (uint32_t)t, (uint32_t)P.it, nz);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int d = 4 * j + i;
+                            if (d >= D) break;
+                            const float mu = Hd[d * kTileRows + r];
+                            float lv = Hd[(D + d) * kTileRows + r];
+                            const float dmu = mu * v_dscale[d] + v_dmean[d];
+                            float delta = dmu;
+                            if (!P.deterministic) {
+                                lv = bounded_logvar(lv, v_maxlv[d], v_minlv[d]);
+                                delta = dmu + nz[i] * expf((lv + v_2logstd[d]) / 2.0f);
+                            }
+                            float* sp = S + r * (D + 1) + d;
+                            const float sn = env_postproc(P.env_id, *sp, delta, d);
+                            *sp = sn;
+                            if (P.row_mode == kRowsPlanner) {
+                                if (P.states != nullptr)
+                                    P.states[(((size_t)t * P.m * P.n_local + r_src[r]) * P.p + r_pi[r]) * D + d] = sn;
+                            } else {
+                                const size_t o = (size_t)r_src[r] * D + d;
+                                if (P.next_obs) P.next_obs[o] = sn;
+                                if (P.mu_out) P.mu_out[o] = mu;
+                                if (P.lv_out) P.lv_out[o] = lv;
+                            }
+                        }
+                    }
+                }
+                ptx::bar_sync(1, kEpiThreads);
+            }
+            if (P.row_mode == kRowsPlanner && group == 0 && valid) {
+                if (env_reward_reads_next(P.env_id)) ret += env_reward_next(P.env_id, S + row * (D + 1));
+                P.ret_p[(size_t)r_src[row] * P.p + r_pi[row]] = ret;
+            }
+        }
+    }
+
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+static int g_tc_smem = 0;
+
+cudaError_t launch_rollout_tc(RolloutParams P, const unsigned char* wimg, long long wimg_member_stride, int terms,
+                              int num_sms, cudaStream_t stream, const char** name) {
+    TcParams T{};
+    T.wimg = wimg;
+    T.wimg_member_stride = wimg_member_stride;
+    T.Np = round_up(P.H, 16);
+    T.NHp = round_up(2 * P.D, 16);
+    T.nkb0 = round_up(P.In, 16) / 16;
+    T.nkbH = T.Np / 16;
+    T.terms = terms;
+    int tiles = (P.rows_per_member + kTileRows - 1) / kTileRows;
+    P.rows_per_cta = (P.rows_per_member + tiles - 1) / tiles;            // balance the rows over the tiles
+    tiles = (P.rows_per_member + P.rows_per_cta - 1) / P.rows_per_cta;
+    T.tiles_per_member = tiles;
+    T.total_tiles = tiles * P.E;
+    // shared-memory ring: as many stages as fit in 227 KB
+    int stages = 8;
+    while (stages > 2 && tc_smem_layout(P.D, P.n_hidden, T.Np, T.NHp, stages).total > 227 * 1024) --stages;
+    T.stages = stages;
+    const TcSmem L = tc_smem_layout(P.D, P.n_hidden, T.Np, T.NHp, stages);
+    if (L.total > 227 * 1024) return cudaErrorInvalidConfiguration;
+    T.R = P;
+    if ((int)L.total > g_tc_smem) {
+        cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        if (e != cudaSuccess) return e;
+        g_tc_smem = (int)L.total;
+    }
+    if (name) *name = terms == 3 ? "rollout_tc_kernel(f16hi+bf16lo x3)" : "rollout_tc_kernel(f16 x1)";
+    const int grid = min(T.total_tiles, num_sms);
+    rollout_tc_kernel<<<grid, kTcThreads, L.total, stream>>>(T);
+    return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Self-test: ONE 128 x N x K product with exactly the operand layouts, descriptors and split arithmetic of the rollout
+// kernel (device diagnostic behind cadm_selftest_tc_gemm; tests compare it with an fp64 matmul).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) tc_gemm_selftest_kernel(const float* __restrict__ X, const unsigned char* wimg,
+                                                                   int K, int N, int terms, float* __restrict__ out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* xhi = smem;
+    unsigned char* xlo = smem + kXBytes;
+    unsigned char* wst = smem + 2 * kXBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kXBytes + kMaxStageBytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nkb = (K + 15) / 16;
+    if (tid == 0) {
+        ptx::mbar_init(&bars[0], 1);
+        ptx::mbar_init(&bars[1], 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(tmem_slot, 256);
+        tc::tmem_relinquish();
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int k = kb * 16 + j;
+            y[j] = k < K ? X[(size_t)tid * K + k] : 0.f;
+        }
+        store_block16(xhi, xlo, kb, tid, y);
+    }
+    ptx::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {
+        const uint32_t bytes = 2u * N * 32u;
+        const uint32_t xhi_a = ptx::smem_u32(xhi), xlo_a = ptx::smem_u32(xlo), w_a = ptx::smem_u32(wst);
+        uint32_t ph = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_arrive_expect_tx(&bars[0], bytes);
+            ptx::bulk_g2s(wst, wimg + (size_t)kb * bytes, bytes, &bars[0]);
+            ptx::mbar_wait(&bars[0], ph);
+            tc::fence_after_sync();
+            const uint64_t a_hi = tc::smem_desc(xhi_a + 2 * kb * kXChunkBytes, kXChunkBytes, 128);
+            const uint64_t a_lo = tc::smem_desc(xlo_a + 2 * kb * kXChunkBytes, kXChunkBytes, 128);
+            const uint64_t b_hi = tc::smem_desc(w_a, 16 * N, 128);
+            const uint64_t b_lo = tc::smem_desc(w_a + N * 32, 16 * N, 128);
+            tc::mma_f16_ss(tmem_base, a_hi, b_hi, tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N), kb > 0 ? 1u : 0u);
+            if (terms == 3) {
+                tc::mma_f16_ss(tmem_base, a_hi, b_lo, tc::idesc_f16(tc::kFmtF16, tc::kFmtBF16, N), 1u);
+                tc::mma_f16_ss(tmem_base, a_lo, b_hi, tc::idesc_f16(tc::kFmtBF16, tc::kFmtF16, N), 1u);
+            }
+            tc::mma_commit(&bars[1]);
+            ptx::mbar_wait(&bars[1], ph);          // serialise: the single weight slot is reused
+            ph ^= 1u;
+        }
+    }
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < N; c += 8) {
+        uint32_t v[8];
+        tc::tmem_ld8(tl + c, v);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[(size_t)tid * N + c + j] = __uint_as_float(v[j]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
+cudaError_t launch_tc_gemm_selftest(const float* X, const unsigned char* wimg, int K, int N, int terms, float* out,
+                                    cudaStream_t stream) {
+    const int smem_bytes = 2 * kXBytes + kMaxStageBytes + 64;
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    tc_gemm_selftest_kernel<<<1, 128, smem_bytes, stream>>>(X, wimg, K, N, terms, out);
+    return cudaGetLastError();
+}
+
+}  // namespace cadm

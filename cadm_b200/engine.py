@@ -283,6 +283,10 @@ class PlannerEngine:
             self._chk(self.lib.cadm_cem_finish(self._h, _ptr(mean), _ptr(var), _ptr(rets), _ptr(el), self._stream()))
         return dict(mean=mean, var=var, returns=rets, elites=el)
 
+    def set_precision(self, precision: str):
+        self._chk(self.lib.cadm_set_precision(self._h, _lib.PRECISIONS[precision]))
+        self.cfg.precision = precision
+
     # ------------------------------------------------------------------ instrumentation
     @property
     def launch_count(self) -> int:
@@ -297,3 +301,16 @@ class PlannerEngine:
 
     def last_rollout_ms(self) -> float:
         return float(self.lib.cadm_last_rollout_ms(self._h))
+
+
+def selftest_tc_gemm(X: torch.Tensor, W: torch.Tensor, terms: int = 3) -> torch.Tensor:
+    """out[128, N] = X[128, K] @ W[K, N] on the tensor-core path of the rollout kernel (device diagnostic)."""
+    lib = _lib.load()
+    X = X.to(dtype=torch.float32).contiguous()
+    W = W.to(dtype=torch.float32).contiguous()
+    assert X.is_cuda and W.is_cuda and X.shape[0] == 128 and X.shape[1] == W.shape[0]
+    out = torch.empty((128, W.shape[1]), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        check(None, lib.cadm_selftest_tc_gemm(_ptr(X), _ptr(W), X.shape[1], W.shape[1], terms, _ptr(out),
+                                              C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)))
+    return out

@@ -176,6 +176,14 @@ int cadm_plan_rs(void* handle, int32_t m, const float* obs, const float* cp_obs,
                  uint64_t seed, const float* u, const int32_t* u_int, const float* eps,
                  float* action, int32_t* action_int, float* returns, int32_t* best, void* stream);
 
+/* Switch the arithmetic of the MLP contractions at run time (CADM_PREC_*); both weight images are kept packed. */
+int cadm_set_precision(void* handle, int32_t precision);
+
+/* Device self-test of the tensor-core path: out[128, N] = X[128, K] * W[K, N] computed with exactly the operand layouts,
+ * descriptors and hi/lo split of the rollout kernel (terms = 3: CADM_PREC_TC_3X arithmetic, 1: CADM_PREC_TC_1X).
+ * K <= 208, N a multiple of 16 <= 208.  Synchronises.  Diagnostic only. */
+int cadm_selftest_tc_gemm(const float* X, const float* W, int32_t K, int32_t N, int32_t terms, float* out, void* stream);
+
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t cadm_launch_count(void* handle);
 /* Name of the rollout kernel variant in use, e.g. "rollout_f32<32>" (for reports). */
