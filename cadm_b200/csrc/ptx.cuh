@@ -132,16 +132,29 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- fp32 -> (fp16 hi, bf16 lo) split, two values at a time --------------------------------------
-// x = hi + lo with hi = fp16(x) (saturating) and lo = bf16(x - hi): ~19-20 significant bits, bf16 range for lo.
+// ---- fp32 -> (fp16 hi, fp16 lo) split, two values at a time ----------------------------------------
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (both saturating).  Error <= max(2^-22 |x|, 2^-25): the residual
+// may be an fp16 subnormal (absolute spacing 2^-24), so operands are pre-scaled by powers of two (kXScale, kWScale)
+// to keep typical residuals in the normal range.  A and B of one tcgen05.mma must share a format (mixing f16 with
+// bf16 traps as an illegal instruction on sm_100a), hence fp16 for both halves.
+constexpr float kXScale = 8.0f;        // activations are stored as 8 x
+constexpr float kWScale = 64.0f;       // weights are stored as 64 w     -> accumulators hold 512 x.w
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     uint32_t h;
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));   // low half <- x0
     float h0, h1;
     asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}" : "=f"(h0), "=f"(h1) : "r"(h));
     const float r0 = x0 - h0, r1 = x1 - h1;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
     hi = h;
+}
+
+// 8 * swish(x) given x8 = 8 x:  x8 * sigmoid(x8 / 8), with ex2.approx / rcp.approx (each <= 2 ulp)
+__device__ __forceinline__ float swish8_fast(float x8) {
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x8 * (-1.4426950408889634f / 8.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+    return x8 * r;
 }
 
 __device__ __forceinline__ float swish_fast(float x) {

@@ -5,11 +5,12 @@
 // Every layer is D[128 x N] = X[128 x K] * W^T[N x K] on the 5th-gen tensor cores (M = 128, N = 208 / 2D padded, K = 16
 // per instruction, kind::f16, fp32 accumulate in TMEM).
 //
-// Precision (CADM_PREC_TC_3X): every fp32 operand is split as x = hi + lo, hi = fp16(x), lo = bf16(x - hi)
-// (19-20 significant bits, bf16 exponent range for the residual) and a product is 3 MMAs into ONE accumulator:
-//     X_hi * W_hi (f16 x f16)  +  X_hi * W_lo (f16 x bf16)  +  X_lo * W_hi (bf16 x f16)
-// (the A and B formats are separate fields of the instruction descriptor, so mixed f16/bf16 MMAs are legal).  The
-// dropped lo*lo term and the bf16 rounding of lo are ~2^-20 relative -- fp32-class for the 1e-4 parity bar.
+// Precision (CADM_PREC_TC_3X): every fp32 operand is split as x = hi + lo with hi = fp16(x), lo = fp16(x - hi), after
+// a power-of-two pre-scale (activations x 8, weights x 64) that keeps typical residuals out of the fp16 subnormal
+// range; a product is 3 MMAs into ONE fp32 accumulator:   X_hi W_hi + X_hi W_lo + X_lo W_hi.
+// The dropped lo*lo term and the rounding of lo are <= ~2^-21 relative -- fp32-class for the 1e-4 parity bar; the
+// scale 512 is removed exactly in the epilogue.  (A and B of one tcgen05.mma must have the SAME format: an f16 x bf16
+// instruction traps as illegal on sm_100a, which rules out an fp16-hi / bf16-lo split.)
 // CADM_PREC_TC_1X issues only the first MMA (fp16 operands; fast, does not claim the bar).
 //
 // Warp roles (320 threads):
@@ -65,7 +66,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int D, int n_hidden, int Np, in
 // K-major no-swizzle layout: byte(n, kk) = (kk / 8) * (16 N) + 16 n + 2 (kk % 8)
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_tc_kernel(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad,
-                               long long member_stride, long long layer_off, int clear) {
+                               long long member_stride, long long layer_off, int clear, float wscale) {
     const long long per_member = (long long)nkb * Npad * 16;
     const long long total = (long long)E * per_member;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -78,7 +79,7 @@ __global__ void pack_tc_kernel(unsigned char* dst, const float* src, int E, int 
         const int ns = n - col0;
         const bool valid = ns >= 0 && ns < out && k < in;
         if (!valid && !clear) continue;
-        const float w = valid ? src[((size_t)e * in + k) * out + ns] : 0.f;
+        const float w = valid ? src[((size_t)e * in + k) * out + ns] * wscale : 0.f;
         uint32_t hi, lo;
         tc::split2(w, 0.f, hi, lo);
         unsigned char* blk = dst + e * member_stride + layer_off + (long long)kb * (2 * Npad * 32);
@@ -90,9 +91,10 @@ __global__ void pack_tc_kernel(unsigned char* dst, const float* src, int E, int 
 
 cudaError_t launch_pack_tc(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad,
                            long long member_stride, long long layer_off, int clear, cudaStream_t stream) {
+    const float wscale = tc::kWScale;
     const long long total = (long long)E * nkb * Npad * 16;
     pack_tc_kernel<<<(int)min((total + 255) / 256, (long long)2368), 256, 0, stream>>>(dst, src, E, in, out, col0, nkb, Npad,
-                                                                                       member_stride, layer_off, clear);
+                                                                                       member_stride, layer_off, clear, wscale);
     return cudaGetLastError();
 }
 
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
+        __syncwarp();
         tc::tmem_alloc(tmem_slot, 512);
         tc::tmem_relinquish();
     }
@@ -234,9 +237,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                         const int nkb = g == 0 ? T.nkb0 : T.nkbH;
                         const uint32_t N = g == P.n_hidden ? (uint32_t)T.NHp : (uint32_t)T.Np;
                         const uint32_t d_tmem = tmem_base + (g_count & 1u) * 256u;
-                        const uint32_t id_hh = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
-                        const uint32_t id_hl = tc::idesc_f16(tc::kFmtF16, tc::kFmtBF16, N);
-                        const uint32_t id_lh = tc::idesc_f16(tc::kFmtBF16, tc::kFmtF16, N);
+                        const uint32_t idesc = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
                         for (int kb = 0; kb < nkb; ++kb) {
                             ptx::mbar_wait(&x_ready[kb], (xphase >> kb) & 1u);
                             xphase ^= 1u << kb;
@@ -247,10 +248,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                             const uint64_t a_lo = tc::smem_desc(xlo_a + 2 * kb * kXChunkBytes, kXChunkBytes, 128);
                             const uint64_t b_hi = tc::smem_desc(wb, 16 * N, 128);
                             const uint64_t b_lo = tc::smem_desc(wb + N * 32, 16 * N, 128);
-                            tc::mma_f16_ss(d_tmem, a_hi, b_hi, id_hh, kb > 0 ? 1u : 0u);
+                            tc::mma_f16_ss(d_tmem, a_hi, b_hi, idesc, kb > 0 ? 1u : 0u);
                             if (T.terms == 3) {
-                                tc::mma_f16_ss(d_tmem, a_hi, b_lo, id_hl, 1u);
-                                tc::mma_f16_ss(d_tmem, a_lo, b_hi, id_lh, 1u);
+                                tc::mma_f16_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+                                tc::mma_f16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
                             }
                             tc::mma_commit(&w_empty[rc.stage]);
                             rc.advance();
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
             const int tile_row0 = (tile - e * T.tiles_per_member) * P.rows_per_cta;
             const int nrows = min(P.rows_per_cta, P.rows_per_member - tile_row0);
             ptx::bar_sync(1, kEpiThreads);             // previous tile fully retired before its smem is reused
-            for (int i = et; i < P.n_hidden * T.Np + T.NHp; i += kEpiThreads) bias[i] = P.bpack[(size_t)e * P.bias_stride + i];
+            for (int i = et; i < P.n_hidden * T.Np + T.NHp; i += kEpiThreads)      // hidden-layer biases pre-scaled by kXScale
+                bias[i] = P.bpack[(size_t)e * P.bias_stride + i] * (i < P.n_hidden * T.Np ? tc::kXScale : 1.0f);
             if (et < kTileRows) {
                 const int r = et;
                 int mi = 0, src = 0, pi = 0, cidx = 0, rid = 0, er = 0;
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                                 v = __ldg(P.ctx + (size_t)r_ctx[row] * P.C + (k - P.P - A));
                             }
                         }
-                        y[j] = v;
+                        y[j] = v * tc::kXScale;
                     }
                     store_block16(xhi, xlo, kb, row, y);
                     publish_block(&x_ready[kb], lane);
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                         for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
                         if (kb + 1 < kb1) tc::tmem_ld16(tcol + (kb + 1) * 16, v);      // prefetch the next block
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) y[j] = tc::swish_fast(y[j] + bl[kb * 16 + j]);
+                        for (int j = 0; j < 16; ++j) y[j] = tc::swish8_fast(fmaf(y[j], 1.0f / tc::kWScale, bl[kb * 16 + j]));
                         store_block16(xhi, xlo, kb, row, y);
                         tc::fence_before_sync();
                         publish_block(&x_ready[kb], lane);
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                         tc::tmem_ld8(tcol + b * 8, v);
                         tc::tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) Hd[(b * 8 + j) * kTileRows + row] = __uint_as_float(v[j]) + bl[b * 8 + j];
+                        for (int j = 0; j < 8; ++j) Hd[(b * 8 + j) * kTileRows + row] = fmaf(__uint_as_float(v[j]), 1.0f / (tc::kWScale * tc::kXScale), bl[b * 8 + j]);
                     }
                     tc::fence_before_sync();
                 }
@@ -470,7 +472,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
 
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -529,7 +534,8 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_selftest_kernel(const float* _
         ptx::mbar_init(&bars[1], 1);
         ptx::fence_mbar_init();
     }
-    if (warp == 0) {
+    if (warp == 1) {                      // a fully converged warp (warp 0 just diverged on tid == 0)
+        __syncwarp();
         tc::tmem_alloc(tmem_slot, 256);
         tc::tmem_relinquish();
     }
@@ -538,7 +544,7 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_selftest_kernel(const float* _
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int k = kb * 16 + j;
-            y[j] = k < K ? X[(size_t)tid * K + k] : 0.f;
+            y[j] = k < K ? X[(size_t)tid * K + k] * tc::kXScale : 0.f;
         }
         store_block16(xhi, xlo, kb, tid, y);
     }
@@ -560,10 +566,11 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_selftest_kernel(const float* _
             const uint64_t a_lo = tc::smem_desc(xlo_a + 2 * kb * kXChunkBytes, kXChunkBytes, 128);
             const uint64_t b_hi = tc::smem_desc(w_a, 16 * N, 128);
             const uint64_t b_lo = tc::smem_desc(w_a + N * 32, 16 * N, 128);
-            tc::mma_f16_ss(tmem_base, a_hi, b_hi, tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N), kb > 0 ? 1u : 0u);
+            const uint32_t idesc = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
+            tc::mma_f16_ss(tmem_base, a_hi, b_hi, idesc, kb > 0 ? 1u : 0u);
             if (terms == 3) {
-                tc::mma_f16_ss(tmem_base, a_hi, b_lo, tc::idesc_f16(tc::kFmtF16, tc::kFmtBF16, N), 1u);
-                tc::mma_f16_ss(tmem_base, a_lo, b_hi, tc::idesc_f16(tc::kFmtBF16, tc::kFmtF16, N), 1u);
+                tc::mma_f16_ss(tmem_base, a_hi, b_lo, idesc, 1u);
+                tc::mma_f16_ss(tmem_base, a_lo, b_hi, idesc, 1u);
             }
             tc::mma_commit(&bars[1]);
             ptx::mbar_wait(&bars[1], ph);          // serialise: the single weight slot is reused
@@ -578,11 +585,14 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_selftest_kernel(const float* _
         tc::tmem_ld8(tl + c, v);
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) out[(size_t)tid * N + c + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 8; ++j) out[(size_t)tid * N + c + j] = __uint_as_float(v[j]) * (1.0f / (tc::kWScale * tc::kXScale));
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, 256);
+    }
 }
 
 cudaError_t launch_tc_gemm_selftest(const float* X, const unsigned char* wimg, int K, int N, int terms, float* out,

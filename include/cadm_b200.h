@@ -42,8 +42,8 @@ extern "C" {
 
 /* arithmetic of the MLP contractions */
 #define CADM_PREC_FP32   0  /* fp32 FFMA: the exact-fp32 path */
-#define CADM_PREC_TC_3X  1  /* tcgen05 tensor cores, split-fp16 x3 (fp32-class accuracy) */
-#define CADM_PREC_TC_1X  2  /* tcgen05 tensor cores, single bf16 pass (fast; does NOT meet the 1e-4 bar) */
+#define CADM_PREC_TC_3X  1  /* tcgen05 tensor cores, fp16 hi/lo split, 3 MMAs per product (fp32-class accuracy) */
+#define CADM_PREC_TC_1X  2  /* tcgen05 tensor cores, single fp16 pass (fast; does NOT meet the 1e-4 bar) */
 
 /* how a particle is paired with a context-encoder member */
 #define CADM_CTX_REFERENCE 0  /* reproduce cadm/dynamics/core/utils.py:433-439 exactly (quirks Q2, Q3) */

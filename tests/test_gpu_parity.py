@@ -22,7 +22,7 @@ def _model(config, m_max=4, **kw):
     return build_model(config, m_max=m_max, **kw)
 
 
-@pytest.fixture(scope="module", params=["fp32"])
+@pytest.fixture(scope="module", params=["fp32", "tc3x"])
 def precision(request):
     return request.param
 
