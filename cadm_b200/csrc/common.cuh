@@ -147,6 +147,25 @@ __device__ __forceinline__ float bounded_logvar(float lv, float max_lv, float mi
     return lv;
 }
 
+// MUFU-based variants for the tensor-core path (ex2.approx / lg2.approx: ~2^-22 relative; the 1e-4 bar has 2 orders of
+// headroom and the fp32 path keeps the libdevice versions)
+__device__ __forceinline__ float fast_exp(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+__device__ __forceinline__ float fast_log(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.6931471805599453f;
+}
+__device__ __forceinline__ float fast_softplus(float x) { return fmaxf(x, 0.f) + fast_log(1.0f + fast_exp(-fabsf(x))); }
+__device__ __forceinline__ float fast_bounded_logvar(float lv, float max_lv, float min_lv) {
+    lv = max_lv - fast_softplus(max_lv - lv);
+    lv = min_lv + fast_softplus(lv - min_lv);
+    return lv;
+}
+
 // planner row -> (mi, nl, pi); rl indexes the rows of member e in the order j*m*n_local + mi*n_local + nl
 __device__ __forceinline__ void planner_row(const RolloutParams& P, int e, int rl, int& mi, int& nl, int& pi) {
     int mn = P.m * P.n_local;

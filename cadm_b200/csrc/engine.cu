@@ -32,6 +32,7 @@ struct Engine {
     int Np16 = 0, NHp16 = 0, nkb0 = 0, nkbH = 0;
     long long wimg_member_stride = 0, bias_stride_tc = 0;
     int precision = CADM_PREC_FP32;
+    long long* dbg = nullptr;        // clock64 trace of the tensor-core kernel (diagnostic)
     float* max_lv = nullptr;
     float* min_lv = nullptr;
     bool have_weights = false, have_encoder = false, have_norm = false;
@@ -144,7 +145,7 @@ int run_rollout(Engine* E, RolloutParams& P, cudaStream_t s) {
             P.bpack = E->bpack_tc;
             P.bias_stride = E->bias_stride_tc;
             CU(E, launch_rollout_tc(P, E->wimg, E->wimg_member_stride, E->precision == CADM_PREC_TC_3X ? 3 : 1, E->num_sms, s,
-                                    &E->kernel_name));
+                                    &E->kernel_name, E->timing ? E->dbg : nullptr));
             break;
         default:
             return fail(E, CADM_ERR_UNSUPPORTED, "unknown precision mode");
@@ -264,6 +265,7 @@ int cadm_plan_create(const CadmConfig* cfg, void** handle) {
     A(dalloc(E, &E->returns_log, (size_t)c.cem_iters * mm * c.candidates));
     A(dalloc(E, &E->elites_log, (size_t)c.cem_iters * mm * c.num_elites));
     A(dalloc(E, &E->best, mm));
+    A(dalloc(E, &E->dbg, 64 * 64));
     if (e != cudaSuccess) {
         std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(e);
         for (void* p : E->allocs) cudaFree(p);
@@ -654,6 +656,26 @@ int cadm_selftest_tc_gemm(const float* X, const float* W, int32_t K, int32_t N, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     cudaFree(img);
     if (e != cudaSuccess) return fail(nullptr, CADM_ERR_CUDA, cudaGetErrorString(e));
+    return CADM_OK;
+}
+
+int cadm_selftest_tc_rate(int32_t N, int32_t n_mma, int32_t a_lbo, int64_t* cycles_host) {
+    if (N < 16 || N > 208 || N % 16 || n_mma < 1 || !cycles_host) return fail(nullptr, CADM_ERR_ARG, "bad arguments");
+    long long* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 2 * sizeof(long long));
+    if (e == cudaSuccess) e = launch_tc_mma_rate(N, n_mma, a_lbo, d, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(nullptr, CADM_ERR_CUDA, cudaGetErrorString(e));
+    return CADM_OK;
+}
+
+int cadm_debug_trace(void* handle, int64_t* out_host, int32_t count) {
+    Engine* E = H(handle);
+    if (!E || !out_host || count < 1 || count > 64 * 64) return CADM_ERR_ARG;
+    CU(E, cudaDeviceSynchronize());
+    CU(E, cudaMemcpy(out_host, E->dbg, (size_t)count * sizeof(long long), cudaMemcpyDeviceToHost));
     return CADM_OK;
 }
 

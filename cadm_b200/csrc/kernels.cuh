@@ -60,9 +60,10 @@ cudaError_t launch_pack_bias(float* dst, const float* src, int E, int out, int c
                              cudaStream_t stream);
 cudaError_t launch_rollout_f32(RolloutParams P, int num_sms, cudaStream_t stream, const char** name);
 cudaError_t launch_rollout_tc(RolloutParams P, const unsigned char* wimg, long long wimg_member_stride, int terms,
-                              int num_sms, cudaStream_t stream, const char** name);
+                              int num_sms, cudaStream_t stream, const char** name, long long* dbg);
 cudaError_t launch_pack_tc(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad,
                            long long member_stride, long long layer_off, int clear, cudaStream_t stream);
+cudaError_t launch_tc_mma_rate(int N, int n_mma, int a_lbo, long long* cycles, cudaStream_t stream);
 cudaError_t launch_tc_gemm_selftest(const float* X, const unsigned char* wimg, int K, int N, int terms, float* out,
                                     cudaStream_t stream);
 

@@ -52,6 +52,23 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint32_t j, uint32_t rid,
     box_muller(w.z, w.w, out[2], out[3]);
 }
 
+// same stream with MUFU transcendentals (lg2 / sqrt / sin / cos .approx): |error| ~ 1e-6 absolute per normal
+__device__ __forceinline__ void box_muller_fast(uint32_t wa, uint32_t wb, float& n0, float& n1) {
+    float l, r, s, c;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u01(wa)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * (-2.0f * 0.6931471805599453f)));
+    const float th = 6.283185307179586f * (u01(wb) - 0.5f);        // theta - pi, in [-pi, pi)
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
+    n0 = -r * c;                                                    // cos(theta) = -cos(theta - pi)
+    n1 = -r * s;
+}
+__device__ __forceinline__ void normal4_fast(uint64_t seed, uint32_t j, uint32_t rid, uint32_t t, uint32_t it, float out[4]) {
+    uint4 w = philox(seed, j, rid, t, (it << 8) | kStreamEps);
+    box_muller_fast(w.x, w.y, out[0], out[1]);
+    box_muller_fast(w.z, w.w, out[2], out[3]);
+}
+
 __device__ __forceinline__ uint32_t word_of(const uint4& w, int lane) {
     return lane == 0 ? w.x : lane == 1 ? w.y : lane == 2 ? w.z : w.w;
 }

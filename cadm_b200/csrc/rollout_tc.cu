@@ -31,8 +31,9 @@
 
 namespace cadm {
 
-constexpr int kTcThreads = 320;
-constexpr int kEpiThreads = 256;
+constexpr int kEpiGroups = 4;                  // epilogue warp groups; each group = 4 warps = the 4 TMEM lane quarters
+constexpr int kEpiThreads = kEpiGroups * 128;
+constexpr int kTcThreads = 64 + kEpiThreads;
 constexpr int kTileRows = 128;
 constexpr int kMaxKB = 13;                     // K16 blocks of the widest layer (208 / 16)
 constexpr int kXChunkBytes = 2048;             // one 8-wide k-chunk of all 128 rows: 128 rows x 16 B
@@ -40,25 +41,51 @@ constexpr int kXBytes = 2 * kMaxKB * kXChunkBytes;   // 53248 per operand half (
 constexpr int kMaxStageBytes = 2 * 208 * 32;   // hi + lo block of one K16 step, N = 208
 
 struct TcSmem {
-    size_t off_xhi, off_xlo, off_w, off_s, off_bias, off_vec, off_rowi, off_bar, total;
+    size_t off_xhi, off_xlo, off_w, off_s, off_bias, off_vec, off_rowi, off_feat, off_act, off_ctx, off_bar, total;
     int stages;
 };
 
-__host__ __device__ inline TcSmem tc_smem_layout(int D, int n_hidden, int Np, int NHp, int stages) {
+__host__ __device__ inline TcSmem tc_smem_layout(int D, int A, int C, int n_hidden, int Np, int NHp, int stages) {
     TcSmem L;
     size_t o = 0;
     L.off_xhi = o; o += kXBytes;
     L.off_xlo = o; o += kXBytes;
     L.off_w = o; o += (size_t)stages * kMaxStageBytes;
     L.off_s = o; o += (size_t)round_up(kTileRows * (D + 1), 4) * 4;
+    o = (o + 15) / 16 * 16;
     L.off_bias = o; o += (size_t)round_up(n_hidden * Np + NHp, 4) * 4;
     L.off_vec = o; o += (size_t)(2 * kMaxObs + 2 * kMaxAct + 5 * kMaxObs) * 4;
     L.off_rowi = o; o += (size_t)kTileRows * 6 * 4;
+    L.off_feat = o; o += (size_t)96 * 16;                       // layer-0 feature table (In <= 84, padded to 96)
+    L.off_act = o; o += (size_t)2 * kTileRows * A * 4;          // this step's / next step's actions of the tile rows
+    L.off_ctx = o; o += (size_t)kTileRows * C * 4;              // context vector of every tile row
     o = (o + 15) / 16 * 16;
     L.off_bar = o; o += (size_t)(2 * 8 + kMaxKB + 2 + 2) * 8;     // w_full[8], w_empty[8], x_ready[13], acc_full[2], tmem slot
     L.total = o;
     L.stages = stages;
     return L;
+}
+
+// K16 blocks of a layer are split between the epilogue groups (group g owns blocks [first(g), first(g+1))) and the MMA
+// warp consumes them round-robin over the groups -- the order in which they become ready.  blk_of_pos / pos_of_blk map
+// between the natural block index kb and the position in that consumption order (also the order of the weight stream).
+__host__ __device__ inline int grp_first(int nkb, int g) { return (nkb * g + kEpiGroups - 1) / kEpiGroups; }
+__host__ __device__ inline int blk_of_pos(int nkb, int pos) {
+    int round = 0, seen = 0;
+    for (;; ++round) {
+        for (int g = 0; g < kEpiGroups; ++g) {
+            const int kb = grp_first(nkb, g) + round;
+            if (kb < grp_first(nkb, g + 1)) {
+                if (seen == pos) return kb;
+                ++seen;
+            }
+        }
+    }
+}
+__host__ __device__ inline int pos_of_blk(int nkb, int kb) {
+    for (int pos = 0; pos < nkb; ++pos)
+        if (blk_of_pos(nkb, pos) == kb) return pos;
+    return -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -82,7 +109,7 @@ __global__ void pack_tc_kernel(unsigned char* dst, const float* src, int E, int 
         const float w = valid ? src[((size_t)e * in + k) * out + ns] * wscale : 0.f;
         uint32_t hi, lo;
         tc::split2(w, 0.f, hi, lo);
-        unsigned char* blk = dst + e * member_stride + layer_off + (long long)kb * (2 * Npad * 32);
+        unsigned char* blk = dst + e * member_stride + layer_off + (long long)pos_of_blk(nkb, kb) * (2 * Npad * 32);
         const int off = (kk >> 3) * (16 * Npad) + 16 * n + 2 * (kk & 7);
         *reinterpret_cast<unsigned short*>(blk + off) = (unsigned short)(hi & 0xffffu);
         *reinterpret_cast<unsigned short*>(blk + Npad * 32 + off) = (unsigned short)(lo & 0xffffu);
@@ -128,6 +155,13 @@ __device__ __forceinline__ void publish_block(uint64_t* bar, int lane) {
     if (lane == 0) ptx::mbar_arrive(bar);
 }
 
+// 4-byte async copy global -> shared (LDGSTS) and its group fences
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 struct TcParams {
     RolloutParams R;
     const unsigned char* wimg;   // packed tensor-core weight image
@@ -139,12 +173,15 @@ struct TcParams {
     int terms;                   // 3 (hi/lo split) or 1
     int stages;
     int tiles_per_member, total_tiles;
+    long long* dbg;              // nullable: clock64 trace of CTA 0, [step][64]
+    unsigned char order0[16];    // MMA consumption order of the K16 blocks of layer 0 ...
+    unsigned char orderH[16];    // ... and of the other layers (kernel-parameter space -> uniform loads)
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_constant__ TcParams T) {
     const RolloutParams& P = T.R;
     extern __shared__ __align__(1024) unsigned char smem[];
-    const TcSmem L = tc_smem_layout(P.D, P.n_hidden, T.Np, T.NHp, T.stages);
+    const TcSmem L = tc_smem_layout(P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, T.stages);
     unsigned char* xhi = smem + L.off_xhi;
     unsigned char* xlo = smem + L.off_xlo;
     unsigned char* wring = smem + L.off_w;
@@ -152,6 +189,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
     float* bias = reinterpret_cast<float*>(smem + L.off_bias);
     float* vec = reinterpret_cast<float*>(smem + L.off_vec);
     int* rowi = reinterpret_cast<int*>(smem + L.off_rowi);
+    float4* feat = reinterpret_cast<float4*>(smem + L.off_feat);     // per layer-0 feature: {kind, index, mean, 1/(std+1e-10)}
+    float* act_s = reinterpret_cast<float*>(smem + L.off_act);
+    float* ctx_s = reinterpret_cast<float*>(smem + L.off_ctx);
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* w_empty = w_full + 8;
     uint64_t* x_ready = w_empty + 8;
@@ -178,8 +218,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
     const int warp = tid >> 5, lane = tid & 31;
     const int nstage = T.stages;
     const int gemms_per_step = P.n_hidden + 1;
-    const int kb_split = T.nkbH / 2;               // epilogue group A: blocks [0, kb_split), group B: the rest
-
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
         for (int k = 0; k < kMaxKB; ++k) ptx::mbar_init(&x_ready[k], 4);
@@ -225,40 +263,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
         }
     }
     // ======================= warp 1: MMA issuer ==================================================
+    // The whole warp walks the schedule with warp-uniform state (so descriptors live in uniform registers); one elected
+    // lane issues the tcgen05 instructions.  (Issuing from inside `if (lane == 0)` makes ptxas wrap every UTCHMMA in an
+    // ELECT + 7 x R2UR waterfall loop: ~160 cycles per MMA, slower than the tensor pipe itself.)
     else if (warp == 1) {
-        if (lane == 0) {
-            Ring rc{0, 0, nstage};
-            uint32_t xphase = 0;          // bit kb = parity to wait for on x_ready[kb]
-            uint32_t g_count = 0;         // running GEMM index: accumulator buffer = g & 1
-            const uint32_t xhi_a = ptx::smem_u32(xhi), xlo_a = ptx::smem_u32(xlo), w_a = ptx::smem_u32(wring);
-            for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
-                for (int t = 0; t < P.h; ++t) {
-                    for (int g = 0; g < gemms_per_step; ++g) {
-                        const int nkb = g == 0 ? T.nkb0 : T.nkbH;
-                        const uint32_t N = g == P.n_hidden ? (uint32_t)T.NHp : (uint32_t)T.Np;
-                        const uint32_t d_tmem = tmem_base + (g_count & 1u) * 256u;
-                        const uint32_t idesc = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
-                        for (int kb = 0; kb < nkb; ++kb) {
-                            ptx::mbar_wait(&x_ready[kb], (xphase >> kb) & 1u);
-                            xphase ^= 1u << kb;
-                            ptx::mbar_wait(&w_full[rc.stage], rc.phase);
-                            tc::fence_after_sync();
-                            const uint32_t wb = w_a + rc.stage * kMaxStageBytes;
-                            const uint64_t a_hi = tc::smem_desc(xhi_a + 2 * kb * kXChunkBytes, kXChunkBytes, 128);
-                            const uint64_t a_lo = tc::smem_desc(xlo_a + 2 * kb * kXChunkBytes, kXChunkBytes, 128);
-                            const uint64_t b_hi = tc::smem_desc(wb, 16 * N, 128);
-                            const uint64_t b_lo = tc::smem_desc(wb + N * 32, 16 * N, 128);
-                            tc::mma_f16_ss(d_tmem, a_hi, b_hi, idesc, kb > 0 ? 1u : 0u);
+        Ring rc{0, 0, nstage};
+        uint32_t xphase = 0;          // bit kb = parity to wait for on x_ready[kb]
+        uint32_t g_count = 0;         // running GEMM index: accumulator buffer = g & 1
+        const uint32_t xhi_a = ptx::smem_u32(xhi), xlo_a = ptx::smem_u32(xlo), w_a = ptx::smem_u32(wring);
+        const uint32_t desc_hi_const = (1u << 14) | 8u;             // version 1 (bit 46), SBO = 128 B  (upper 32 bits)
+        for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
+            for (int t = 0; t < P.h; ++t) {
+                for (int g = 0; g < gemms_per_step; ++g) {
+                    const int nkb = g == 0 ? T.nkb0 : T.nkbH;
+                    const uint32_t N = g == P.n_hidden ? (uint32_t)T.NHp : (uint32_t)T.Np;
+                    const uint32_t d_tmem = tmem_base + (g_count & 1u) * 256u;
+                    const uint32_t idesc = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
+                    const uint32_t b_lbo = (N >> 0) << 16;          // LBO = 16 N bytes -> (16 N) >> 4 = N, at bits [16, 30)
+                    long long* dbg = (T.dbg && blockIdx.x == 0 && lane == 0 && tile == (int)blockIdx.x && t < 64 && g < 5)
+                                         ? T.dbg + t * 64 + 32 + 4 * g : nullptr;
+                    long long xw = 0, ww = 0;
+                    for (int pos = 0; pos < nkb; ++pos) {
+                        const int kb = g == 0 ? T.order0[pos] : T.orderH[pos];
+                        const long long c0 = dbg ? clock64() : 0;
+                        ptx::mbar_wait(&x_ready[kb], (xphase >> kb) & 1u);
+                        const long long c1 = dbg ? clock64() : 0;
+                        if (dbg && pos == 0) dbg[0] = c1;
+                        xphase ^= 1u << kb;
+                        ptx::mbar_wait(&w_full[rc.stage], rc.phase);
+                        if (dbg) { xw += c1 - c0; ww += clock64() - c1; }
+                        tc::fence_after_sync();
+                        const uint32_t wb = w_a + rc.stage * kMaxStageBytes;
+                        // descriptors: low word = addr >> 4 | LBO >> 4 << 16 ; high word = SBO >> 4 | version
+                        const uint32_t a_lo32 = ((xhi_a + 2 * kb * kXChunkBytes) >> 4) | ((kXChunkBytes >> 4) << 16);
+                        const uint32_t al_lo32 = ((xlo_a + 2 * kb * kXChunkBytes) >> 4) | ((kXChunkBytes >> 4) << 16);
+                        const uint32_t b_lo32 = (wb >> 4) | b_lbo;
+                        const uint32_t bl_lo32 = ((wb + N * 32) >> 4) | b_lbo;
+                        const uint64_t a_hi = ((uint64_t)desc_hi_const << 32) | a_lo32;
+                        const uint64_t a_lo = ((uint64_t)desc_hi_const << 32) | al_lo32;
+                        const uint64_t b_hi = ((uint64_t)desc_hi_const << 32) | b_lo32;
+                        const uint64_t b_lo = ((uint64_t)desc_hi_const << 32) | bl_lo32;
+                        if (ptx::elect_one()) {
+                            tc::mma_f16_ss(d_tmem, a_hi, b_hi, idesc, pos > 0 ? 1u : 0u);
                             if (T.terms == 3) {
                                 tc::mma_f16_ss(d_tmem, a_hi, b_lo, idesc, 1u);
                                 tc::mma_f16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
                             }
                             tc::mma_commit(&w_empty[rc.stage]);
-                            rc.advance();
                         }
-                        tc::mma_commit(&acc_full[g_count & 1u]);
-                        ++g_count;
+                        __syncwarp();
+                        rc.advance();
                     }
+                    if (ptx::elect_one()) tc::mma_commit(&acc_full[g_count & 1u]);
+                    __syncwarp();
+                    if (dbg) { dbg[1] = clock64(); dbg[2] = xw; dbg[3] = ww; }
+                    ++g_count;
                 }
             }
         }
@@ -267,7 +326,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
     else {
         const int et = tid - 64;                       // 0..255
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-        const int group = (warp - 2) >> 2;             // 0: blocks [0, kb_split), 1: the rest
+        const int group = (warp - 2) >> 2;             // owns the K16 blocks [grp_first(nkb, group), grp_first(nkb, group + 1))
         const int row = quarter * 32 + lane;           // tile row == TMEM lane
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint32_t g_count = 0;
@@ -275,14 +334,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
         const size_t eps_step_stride = (size_t)P.E * P.q * P.m * P.n_global * D;
 
         // one-time: normalisation vectors
-        for (int i = et; i < P.P; i += kEpiThreads) { v_obs_mean[i] = P.obs_mean[i]; v_obs_den[i] = P.obs_std[i] + 1e-10f; }
-        for (int i = et; i < A; i += kEpiThreads) { v_act_mean[i] = P.act_mean[i]; v_act_den[i] = P.act_std[i] + 1e-10f; }
+        for (int i = et; i < P.P; i += kEpiThreads) { v_obs_mean[i] = P.obs_mean[i]; v_obs_den[i] = 1.0f / (P.obs_std[i] + 1e-10f); }
+        for (int i = et; i < A; i += kEpiThreads) { v_act_mean[i] = P.act_mean[i]; v_act_den[i] = 1.0f / (P.act_std[i] + 1e-10f); }
         for (int i = et; i < D; i += kEpiThreads) {
             v_dmean[i] = P.delta_mean[i];
             v_dscale[i] = P.delta_std[i] + 1e-10f;
             v_2logstd[i] = 2.0f * logf(P.delta_std[i]);
             v_maxlv[i] = P.max_lv[i];
             v_minlv[i] = P.min_lv[i];
+        }
+
+        // layer-0 feature table: kind 0 zero pad, 1 state element, 2 sin(state), 3 cos(state), 4 action (normalised),
+        // 5 action / one-hot (raw), 6 context
+        for (int k = et; k < T.nkb0 * 16; k += kEpiThreads) {
+            float kind = 0.f, idx = 0.f, mean = 0.f, inv = 1.f;
+            if (k < P.P) {
+                kind = 1.f; idx = (float)k;
+                if (P.env_id == CADM_ENV_HALFCHEETAH) {          // [o1, sin o2, cos o2, o3:]
+                    if (k == 0) idx = 1.f;
+                    else if (k == 1) { kind = 2.f; idx = 2.f; }
+                    else if (k == 2) { kind = 3.f; idx = 2.f; }
+                } else if (P.env_id == CADM_ENV_ANT) {
+                    idx = (float)(k + 1);                        // o[1:]
+                }
+                mean = P.obs_mean[k]; inv = 1.0f / (P.obs_std[k] + 1e-10f);
+            } else if (k < P.P + A) {
+                const int ai = k - P.P;
+                idx = (float)ai;
+                if (P.discrete) kind = 5.f;
+                else { kind = 4.f; mean = P.act_mean[ai]; inv = 1.0f / (P.act_std[ai] + 1e-10f); }
+            } else if (k < P.In) {
+                kind = 6.f; idx = (float)(k - P.P - A);
+            }
+            feat[k] = make_float4(kind, idx, mean, inv);
         }
 
         for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
@@ -320,65 +404,79 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                 if (r < nrows) v = (P.row_mode == kRowsPlanner) ? P.obs0[r_mi[r] * D + d] : P.obs0[(size_t)r_src[r] * D + d];
                 S[r * (D + 1) + d] = v;
             }
+            for (int i = et; i < kTileRows * P.C; i += kEpiThreads) {          // context of every row (constant over the steps)
+                const int r = i / P.C, c = i - r * P.C;
+                ctx_s[i] = r < nrows ? __ldg(P.ctx + (size_t)r_ctx[r] * P.C + c) : 0.f;
+            }
+            // actions of step 0 (later steps are prefetched one step ahead with cp.async)
+            auto prefetch_actions = [&](int t) {
+                if (P.discrete && P.row_mode == kRowsPlanner) return;
+                float* dst = act_s + (t & 1) * kTileRows * A;
+                for (int i = et; i < nrows * A; i += kEpiThreads) {
+                    const int r = i / A, a = i - r * A;
+                    cp_async4(dst + i, P.actions + ((size_t)r_src[r] * P.h + t) * A + a);
+                }
+                cp_async_commit();
+            };
+            prefetch_actions(0);
+            cp_async_wait_all();
             ptx::bar_sync(1, kEpiThreads);
 
             float ret = 0.f;
             const bool valid = row < nrows;
 #pragma unroll 1
             for (int t = 0; t < P.h; ++t) {
+                long long* dbg = (T.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && tile == (int)blockIdx.x && t < 64) ? T.dbg + t * 64 : nullptr;
+                if (dbg) dbg[0] = clock64();
                 // ---------- prologue: reward of the current state; layer-0 input blocks -----------------
                 const float* s = S + row * (D + 1);
+                const float* arow = act_s + (t & 1) * kTileRows * A + row * A;       // this step's action of my row
+                if (t + 1 < P.h) prefetch_actions(t + 1);                            // lands during this step
+                if (dbg) dbg[13] = clock64();
                 if (group == 0 && valid) {
                     if (env_reward_reads_next(P.env_id)) {
                         if (t > 0) ret += env_reward_next(P.env_id, s);
                     } else {
-                        float a[kMaxAct];
-                        const float* ap = P.actions + ((size_t)r_src[row] * P.h + t) * A;
-#pragma unroll 1
-                        for (int i = 0; i < A; ++i) a[i] = __ldg(ap + i);
-                        ret += env_reward_current(P.env_id, s, a, A, P.max_torque);
+                        ret += env_reward_current(P.env_id, s, arow, A, P.max_torque);
                     }
                 }
-                for (int kb = group; kb < T.nkb0; kb += 2) {      // layer 0: the two groups alternate blocks
+                if (dbg) dbg[14] = clock64();
+                for (int kb = grp_first(T.nkb0, group); kb < grp_first(T.nkb0, group + 1); ++kb) {
                     float y[16];
+                    float sn = 0.f, cs = 1.f;
+                    if (P.env_id == CADM_ENV_HALFCHEETAH && kb == 0) sincosf(s[2], &sn, &cs);
+                    const int onehot = (P.discrete && P.row_mode == kRowsPlanner) ? __ldg(P.actions_int + (size_t)r_src[row] * P.h + t) : -1;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int k = kb * 16 + j;
-                        float v = 0.f;
-                        if (valid && k < P.In) {
-                            if (k < P.P) {
-                                v = __fdiv_rn(env_preproc(P.env_id, s, k) - v_obs_mean[k], v_obs_den[k]);
-                            } else if (k < P.P + A) {
-                                const int ai = k - P.P;
-                                if (P.discrete) {
-                                    if (P.row_mode == kRowsPlanner) v = __ldg(P.actions_int + (size_t)r_src[row] * P.h + t) == ai ? 1.f : 0.f;
-                                    else v = __ldg(P.actions + (size_t)r_src[row] * A + ai);
-                                } else {
-                                    const float av = __ldg(P.actions + ((size_t)r_src[row] * P.h + t) * A + ai);
-                                    v = __fdiv_rn(av - v_act_mean[ai], v_act_den[ai]);
-                                }
-                            } else {
-                                v = __ldg(P.ctx + (size_t)r_ctx[row] * P.C + (k - P.P - A));
-                            }
-                        }
-                        y[j] = v * tc::kXScale;
+                        const float4 f = feat[kb * 16 + j];
+                        const int kind = (int)f.x, idx = (int)f.y;
+                        float src = 0.f;
+                        if (kind == 1) src = s[idx];
+                        else if (kind == 2) src = sn;
+                        else if (kind == 3) src = cs;
+                        else if (kind == 4) src = arow[idx];
+                        else if (kind == 5) src = onehot >= 0 ? (onehot == idx ? 1.f : 0.f) : arow[idx];
+                        else if (kind == 6) src = ctx_s[row * P.C + idx];
+                        y[j] = valid ? (src - f.z) * f.w * tc::kXScale : 0.f;
                     }
+                    if (dbg) dbg[15] = clock64();
                     store_block16(xhi, xlo, kb, row, y);
                     publish_block(&x_ready[kb], lane);
                 }
-
+                if (dbg) dbg[1] = clock64();
                 // ---------- hidden layers: accumulator -> bias + swish -> next layer's A operand ---------
 #pragma unroll 1
                 for (int l = 0; l < P.n_hidden; ++l) {
                     const uint32_t buf = g_count & 1u;
                     ptx::mbar_wait(&acc_full[buf], (g_count >> 1) & 1u);
                     tc::fence_after_sync();
+                    if (dbg && l < 4) dbg[2 + 2 * l] = clock64();
                     ++g_count;
                     const uint32_t tcol = tmem_lane + buf * 256u;
                     const float* bl = bias + l * T.Np;
-                    const int kb0 = group == 0 ? 0 : kb_split, kb1 = group == 0 ? kb_split : T.nkbH;
+                    const int kb0 = grp_first(T.nkbH, group), kb1 = grp_first(T.nkbH, group + 1);
                     uint32_t v[16];
-                    tc::tmem_ld16(tcol + kb0 * 16, v);
+                    if (kb0 < kb1) tc::tmem_ld16(tcol + kb0 * 16, v);
 #pragma unroll 1
                     for (int kb = kb0; kb < kb1; ++kb) {
                         tc::tmem_wait_ld();
@@ -386,12 +484,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
 #pragma unroll
                         for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
                         if (kb + 1 < kb1) tc::tmem_ld16(tcol + (kb + 1) * 16, v);      // prefetch the next block
+                        float bb[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) y[j] = tc::swish8_fast(fmaf(y[j], 1.0f / tc::kWScale, bl[kb * 16 + j]));
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(&bb[j]) = *reinterpret_cast<const float4*>(bl + kb * 16 + j);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) y[j] = tc::swish8_fast(fmaf(y[j], 1.0f / tc::kWScale, bb[j]));
                         store_block16(xhi, xlo, kb, row, y);
                         tc::fence_before_sync();
                         publish_block(&x_ready[kb], lane);
                     }
+                    if (dbg && l < 4) dbg[3 + 2 * l] = clock64();
                 }
 
                 // ---------- heads -> Hd (aliases X_hi once the head GEMM has completed) ------------------
@@ -400,11 +502,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                     ptx::mbar_wait(&acc_full[buf], (g_count >> 1) & 1u);
                     tc::fence_after_sync();
                     ++g_count;
+                    if (dbg) dbg[10] = clock64();
                     float* Hd = reinterpret_cast<float*>(xhi);       // [NHp][128]  (column-major: conflict-free)
                     const uint32_t tcol = tmem_lane + buf * 256u;
                     const float* bl = bias + P.n_hidden * T.Np;
                     const int nb8 = T.NHp / 8;
-                    for (int b = group; b < nb8; b += 2) {
+                    for (int b = group; b < nb8; b += kEpiGroups) {
                         uint32_t v[8];
                         tc::tmem_ld8(tcol + b * 8, v);
                         tc::tmem_wait_ld();
@@ -414,6 +517,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                     tc::fence_before_sync();
                 }
                 ptx::bar_sync(1, kEpiThreads);
+                if (dbg) dbg[11] = clock64();
 
                 // ---------- final epilogue: sample, next state ------------------------------------------
                 {
@@ -431,7 +535,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                                 for (int i = 0; i < 4; ++i)
                                     if (4 * j + i < D) nz[i] = __ldg(ep + i);
                             } else {
-                                normal4(P.seed, (uint32_t)j, (uint32_t)r_rid[r], (uint32_t)t, (uint32_t)P.it, nz);
+                                normal4_fast(P.seed, (uint32_t)j, (uint32_t)r_rid[r], (uint32_t)t, (uint32_t)P.it, nz);
                             }
                         }
 #pragma unroll
@@ -443,8 +547,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                             const float dmu = mu * v_dscale[d] + v_dmean[d];
                             float delta = dmu;
                             if (!P.deterministic) {
-                                lv = bounded_logvar(lv, v_maxlv[d], v_minlv[d]);
-                                delta = dmu + nz[i] * expf((lv + v_2logstd[d]) / 2.0f);
+                                lv = fast_bounded_logvar(lv, v_maxlv[d], v_minlv[d]);
+                                delta = dmu + nz[i] * fast_exp((lv + v_2logstd[d]) * 0.5f);
                             }
                             float* sp = S + r * (D + 1) + d;
                             const float sn = env_postproc(P.env_id, *sp, delta, d);
@@ -461,7 +565,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                         }
                     }
                 }
+                cp_async_wait_all();                       // next step's actions have landed (issued in the prologue)
                 ptx::bar_sync(1, kEpiThreads);
+                if (dbg) dbg[12] = clock64();
             }
             if (P.row_mode == kRowsPlanner && group == 0 && valid) {
                 if (env_reward_reads_next(P.env_id)) ret += env_reward_next(P.env_id, S + row * (D + 1));
@@ -482,8 +588,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
 static int g_tc_smem = 0;
 
 cudaError_t launch_rollout_tc(RolloutParams P, const unsigned char* wimg, long long wimg_member_stride, int terms,
-                              int num_sms, cudaStream_t stream, const char** name) {
+                              int num_sms, cudaStream_t stream, const char** name, long long* dbg) {
     TcParams T{};
+    T.dbg = dbg;
     T.wimg = wimg;
     T.wimg_member_stride = wimg_member_stride;
     T.Np = round_up(P.H, 16);
@@ -496,12 +603,14 @@ cudaError_t launch_rollout_tc(RolloutParams P, const unsigned char* wimg, long l
     tiles = (P.rows_per_member + P.rows_per_cta - 1) / P.rows_per_cta;
     T.tiles_per_member = tiles;
     T.total_tiles = tiles * P.E;
+    for (int i = 0; i < T.nkb0; ++i) T.order0[i] = (unsigned char)blk_of_pos(T.nkb0, i);
+    for (int i = 0; i < T.nkbH; ++i) T.orderH[i] = (unsigned char)blk_of_pos(T.nkbH, i);
     // shared-memory ring: as many stages as fit in 227 KB
     int stages = 8;
-    while (stages > 2 && tc_smem_layout(P.D, P.n_hidden, T.Np, T.NHp, stages).total > 227 * 1024) --stages;
+    while (stages > 2 && tc_smem_layout(P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, stages).total > 226 * 1024) --stages;
     T.stages = stages;
-    const TcSmem L = tc_smem_layout(P.D, P.n_hidden, T.Np, T.NHp, stages);
-    if (L.total > 227 * 1024) return cudaErrorInvalidConfiguration;
+    const TcSmem L = tc_smem_layout(P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, stages);
+    if (L.total > 226 * 1024) return cudaErrorInvalidConfiguration;
     T.R = P;
     if ((int)L.total > g_tc_smem) {
         cudaError_t e = cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
@@ -557,9 +666,10 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_selftest_kernel(const float* _
         const uint32_t bytes = 2u * N * 32u;
         const uint32_t xhi_a = ptx::smem_u32(xhi), xlo_a = ptx::smem_u32(xlo), w_a = ptx::smem_u32(wst);
         uint32_t ph = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int pos = 0; pos < nkb; ++pos) {
+            const int kb = blk_of_pos(nkb, pos);            // the weight stream is stored in consumption order
             ptx::mbar_arrive_expect_tx(&bars[0], bytes);
-            ptx::bulk_g2s(wst, wimg + (size_t)kb * bytes, bytes, &bars[0]);
+            ptx::bulk_g2s(wst, wimg + (size_t)pos * bytes, bytes, &bars[0]);
             ptx::mbar_wait(&bars[0], ph);
             tc::fence_after_sync();
             const uint64_t a_hi = tc::smem_desc(xhi_a + 2 * kb * kXChunkBytes, kXChunkBytes, 128);
@@ -567,7 +677,7 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_selftest_kernel(const float* _
             const uint64_t b_hi = tc::smem_desc(w_a, 16 * N, 128);
             const uint64_t b_lo = tc::smem_desc(w_a + N * 32, 16 * N, 128);
             const uint32_t idesc = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
-            tc::mma_f16_ss(tmem_base, a_hi, b_hi, idesc, kb > 0 ? 1u : 0u);
+            tc::mma_f16_ss(tmem_base, a_hi, b_hi, idesc, pos > 0 ? 1u : 0u);
             if (terms == 3) {
                 tc::mma_f16_ss(tmem_base, a_hi, b_lo, idesc, 1u);
                 tc::mma_f16_ss(tmem_base, a_lo, b_hi, idesc, 1u);
@@ -601,6 +711,63 @@ cudaError_t launch_tc_gemm_selftest(const float* X, const unsigned char* wimg, i
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     tc_gemm_selftest_kernel<<<1, 128, smem_bytes, stream>>>(X, wimg, K, N, terms, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Micro-benchmark: `n_mma` back-to-back tcgen05.mma (M = 128, N, K = 16, kind::f16) on resident shared-memory operands
+// in the rollout kernel's layouts, nothing else running on the SM.  Reports clock64 cycles (issue of first -> commit seen).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int N, int n_mma, int a_lbo, long long* cycles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kXBytes + kMaxStageBytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (2 * kXBytes + kMaxStageBytes) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // 1.0h
+    if (tid == 0) {
+        ptx::mbar_init(&bars[0], 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_alloc(tmem_slot, 256);
+        tc::tmem_relinquish();
+    }
+    ptx::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {
+        const uint32_t x_a = ptx::smem_u32(smem), w_a = ptx::smem_u32(smem + 2 * kXBytes);
+        const uint32_t idesc = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
+        const long long t0 = clock64();
+        for (int i = 0; i < n_mma; ++i) {
+            const int kb = i % kMaxKB;
+            const uint64_t a = tc::smem_desc(x_a + 2 * kb * kXChunkBytes, a_lbo, 128);
+            const uint64_t b = tc::smem_desc(w_a, 16 * N, 128);
+            tc::mma_f16_ss(tmem_base, a, b, idesc, i > 0 ? 1u : 0u);
+        }
+        const long long t1 = clock64();
+        tc::mma_commit(&bars[0]);
+        ptx::mbar_wait(&bars[0], 0);
+        const long long t2 = clock64();
+        cycles[0] = t1 - t0;
+        cycles[1] = t2 - t0;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, 256);
+    }
+}
+
+cudaError_t launch_tc_mma_rate(int N, int n_mma, int a_lbo, long long* cycles, cudaStream_t stream) {
+    const int smem_bytes = 2 * kXBytes + kMaxStageBytes + 64;
+    cudaError_t e = cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    tc_mma_rate_kernel<<<1, 128, smem_bytes, stream>>>(N, n_mma, a_lbo, cycles);
     return cudaGetLastError();
 }
 

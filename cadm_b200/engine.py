@@ -299,6 +299,12 @@ class PlannerEngine:
     def set_timing(self, on: bool):
         self._chk(self.lib.cadm_set_timing(self._h, int(on)))
 
+    def debug_trace(self, steps=30) -> np.ndarray:
+        """clock64 trace [steps, 32] of CTA 0 of the last tensor-core rollout (timing must be enabled)."""
+        out = np.zeros((steps, 64), dtype=np.int64)
+        self._chk(self.lib.cadm_debug_trace(self._h, out.ctypes.data_as(C.c_void_p), steps * 64))
+        return out
+
     def last_rollout_ms(self) -> float:
         return float(self.lib.cadm_last_rollout_ms(self._h))
 

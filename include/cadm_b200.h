@@ -184,6 +184,14 @@ int cadm_set_precision(void* handle, int32_t precision);
  * K <= 208, N a multiple of 16 <= 208.  Synchronises.  Diagnostic only. */
 int cadm_selftest_tc_gemm(const float* X, const float* W, int32_t K, int32_t N, int32_t terms, float* out, void* stream);
 
+/* Diagnostic micro-benchmark: n_mma back-to-back tcgen05.mma (M=128, N, K=16, fp16) on resident shared-memory operands;
+ * cycles_host[0] = issue time, cycles_host[1] = time until the commit is observed (clock64 cycles). */
+int cadm_selftest_tc_rate(int32_t N, int32_t n_mma, int32_t a_lbo, int64_t* cycles_host);
+
+/* Diagnostic: clock64 trace of CTA 0 of the last tensor-core rollout launched with timing enabled, [step][32] slots
+ * (see rollout_tc.cu); copies `count` int64 values to the host.  Synchronises. */
+int cadm_debug_trace(void* handle, int64_t* out_host, int32_t count);
+
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t cadm_launch_count(void* handle);
 /* Name of the rollout kernel variant in use, e.g. "rollout_f32<32>" (for reports). */
