@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--impl", default="cadm_b200", choices=["cadm_b200", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4"])
     ap.add_argument("--m", type=int, default=1)
-    ap.add_argument("--precision", default=os.environ.get("CADM_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("CADM_PRECISION", "tc3x"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cadm_b200" else args.warmup

@@ -87,87 +87,96 @@ __device__ __forceinline__ unsigned long long elite_key(float v, int idx) {
     return ((unsigned long long)(~u) << 32) | (uint32_t)idx;
 }
 
+__device__ __forceinline__ float elite_action(const RefitParams& R, int mi, int ni, int k, int hA, float mu0, float var0) {
+    if (ni >= R.n_offset && ni < R.n_offset + R.n_local)
+        return R.actions[((size_t)mi * R.n_local + (ni - R.n_offset)) * hA + k];
+    // not ours: regenerate from the counter-based stream (identical arithmetic on every rank)
+    float z;
+    if (R.z) z = R.z[((size_t)mi * R.n_global + ni) * hA + k];
+    else {
+        uint4 w = philox(R.seed, (uint32_t)(k >> 2), (uint32_t)ni, (uint32_t)mi, ((uint32_t)R.it << 8) | kStreamZ);
+        z = trunc_normal(word_of(w, k & 3));
+    }
+    return cem_action_value(mu0, var0, z);
+}
+
 __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
-    extern __shared__ unsigned long long keys[];      // [npad]
+    extern __shared__ unsigned long long keys[];      // [npad] then (optionally) the staged elite rows [K][hA] fp32
     __shared__ int s_el[256];
     const int mi = blockIdx.x;
     const int tid = threadIdx.x;
     const int n = R.n_global;
+    const int K = R.k_elites;
+    const int hA = R.h * R.A;
+    float* el = reinterpret_cast<float*>(keys + R.npad);
     for (int i = tid; i < R.npad; i += blockDim.x) {
         unsigned long long key = ~0ull;
         if (i < n) {
-            const int g = i / R.n_local, nl = i - g * R.n_local;
-            const float v = R.returns_buf[((size_t)g * R.m + mi) * R.n_local + nl];
+            float v;
+            if (R.ret_p) {                                  // single rank: fold the particle mean (core/utils.py:170) in
+                const float* r = R.ret_p + ((size_t)mi * n + i) * R.p;
+                float sum = 0.f;
+                for (int q = 0; q < R.p; ++q) sum += r[q];
+                v = sum / (float)R.p;
+            } else {
+                const int g = i / R.n_local, nl = i - g * R.n_local;
+                v = R.returns_buf[((size_t)g * R.m + mi) * R.n_local + nl];
+            }
             if (R.returns_log) R.returns_log[(size_t)mi * n + i] = v;
             key = elite_key(v, i);
         }
         keys[i] = key;
     }
     __syncthreads();
-    // bitonic sort, ascending
-    for (int size = 2; size <= R.npad; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = tid; i < R.npad / 2; i += blockDim.x) {
-                const int lo = 2 * i - (i & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const unsigned long long a = keys[lo], b = keys[hi];
-                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
-            }
-            __syncthreads();
+    if (n <= (int)blockDim.x && !R.mode_rs) {
+        // rank by counting: keys are distinct (the index is part of the key), so rank = #smaller keys
+        if (tid < n) {
+            const unsigned long long mine = keys[tid];
+            int rank = 0;
+#pragma unroll 4
+            for (int jx = 0; jx < n; ++jx) rank += keys[jx] < mine ? 1 : 0;
+            if (rank < K) s_el[rank] = tid;
         }
-    }
-    if (R.mode_rs) {
-        if (tid == 0) R.best[mi] = (int)(keys[0] & 0xffffffffu);
-        return;
-    }
-    const int K = R.k_elites;
-    for (int i = tid; i < K; i += blockDim.x) {
-        const int idx = (int)(keys[i] & 0xffffffffu);
-        s_el[i] = idx;
-        if (R.elites_log) R.elites_log[(size_t)mi * K + i] = idx;
+    } else {
+        // bitonic sort, ascending
+        for (int size = 2; size <= R.npad; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = tid; i < R.npad / 2; i += blockDim.x) {
+                    const int lo = 2 * i - (i & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const unsigned long long a = keys[lo], b = keys[hi];
+                    if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        if (R.mode_rs) {
+            if (tid == 0) R.best[mi] = (int)(keys[0] & 0xffffffffu);
+            return;
+        }
+        for (int i = tid; i < K; i += blockDim.x) s_el[i] = (int)(keys[i] & 0xffffffffu);
     }
     __syncthreads();
-    const int hA = R.h * R.A;
+    for (int i = tid; i < K; i += blockDim.x)
+        if (R.elites_log) R.elites_log[(size_t)mi * K + i] = s_el[i];
+    if (R.stage_elites) {
+        // gather the elite sequences with independent, coalesced loads, then reduce from shared memory
+        for (int i = tid; i < K * hA; i += blockDim.x) {
+            const int jx = i / hA, k = i - jx * hA;
+            el[i] = elite_action(R, mi, s_el[jx], k, hA, R.mean[(size_t)mi * hA + k], R.var[(size_t)mi * hA + k]);
+        }
+        __syncthreads();
+    }
     for (int k = tid; k < hA; k += blockDim.x) {
         const float mu0 = R.mean[(size_t)mi * hA + k];
         const float var0 = R.var[(size_t)mi * hA + k];
         float sum = 0.f;
-        // pass 1: elite mean
-        for (int j = 0; j < K; ++j) {
-            const int ni = s_el[j];
-            float a;
-            if (ni >= R.n_offset && ni < R.n_offset + R.n_local) {
-                a = R.actions[((size_t)mi * R.n_local + (ni - R.n_offset)) * hA + k];
-            } else {
-                // not ours: regenerate from the counter-based stream (identical arithmetic on every rank)
-                float z;
-                if (R.z) z = R.z[((size_t)mi * n + ni) * hA + k];
-                else {
-                    uint4 w = philox(R.seed, (uint32_t)(k >> 2), (uint32_t)ni, (uint32_t)mi, ((uint32_t)R.it << 8) | kStreamZ);
-                    z = trunc_normal(word_of(w, k & 3));
-                }
-                a = cem_action_value(mu0, var0, z);
-            }
-            sum += a;
-        }
+        for (int jx = 0; jx < K; ++jx) sum += R.stage_elites ? el[jx * hA + k] : elite_action(R, mi, s_el[jx], k, hA, mu0, var0);
         const float new_mean = sum / (float)K;
         float sq = 0.f;
-        for (int j = 0; j < K; ++j) {
-            const int ni = s_el[j];
-            float a;
-            if (ni >= R.n_offset && ni < R.n_offset + R.n_local) {
-                a = R.actions[((size_t)mi * R.n_local + (ni - R.n_offset)) * hA + k];
-            } else {
-                float z;
-                if (R.z) z = R.z[((size_t)mi * n + ni) * hA + k];
-                else {
-                    uint4 w = philox(R.seed, (uint32_t)(k >> 2), (uint32_t)ni, (uint32_t)mi, ((uint32_t)R.it << 8) | kStreamZ);
-                    z = trunc_normal(word_of(w, k & 3));
-                }
-                a = cem_action_value(mu0, var0, z);
-            }
-            const float d = a - new_mean;
+        for (int jx = 0; jx < K; ++jx) {
+            const float d = (R.stage_elites ? el[jx * hA + k] : elite_action(R, mi, s_el[jx], k, hA, mu0, var0)) - new_mean;
             sq += d * d;
         }
         const float new_var = sq / (float)K;
@@ -177,14 +186,17 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
 }
 
 static int g_refit_smem = 0;
-cudaError_t launch_refit(const RefitParams& R, cudaStream_t stream) {
-    const size_t smem = (size_t)R.npad * 8;
+cudaError_t launch_refit(RefitParams R, cudaStream_t stream) {
+    size_t smem = (size_t)R.npad * 8;
+    const size_t stage = (size_t)R.k_elites * R.h * R.A * 4;
+    R.stage_elites = (!R.mode_rs && smem + stage <= 200 * 1024) ? 1 : 0;
+    if (R.stage_elites) smem += stage;
     if (smem > 48 * 1024 && (int)smem > g_refit_smem) {
         cudaError_t e = cudaFuncSetAttribute(refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         g_refit_smem = (int)smem;
     }
-    const int threads = R.npad / 2 >= 1024 ? 1024 : max(R.npad / 2, 256);
+    const int threads = R.npad >= 1024 ? 1024 : max(R.npad, 256);
     refit_kernel<<<R.m, threads, smem, stream>>>(R);
     return cudaGetLastError();
 }

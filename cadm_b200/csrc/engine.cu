@@ -491,8 +491,10 @@ int cadm_cem_rollout(void* handle, int32_t it, uint64_t seed, const float* z, co
     P.ret_p = E->ret_p; P.states = nullptr;
     if (int r = run_rollout(E, P, s)) return r;
 
-    CU(E, launch_particle_mean(E->ret_p, E->returns_buf + (size_t)c.rank * m * E->n_local, m * E->n_local, c.particles, s));
-    E->launches++;
+    if (c.world > 1) {      // single rank: the refit kernel folds the particle mean in
+        CU(E, launch_particle_mean(E->ret_p, E->returns_buf + (size_t)c.rank * m * E->n_local, m * E->n_local, c.particles, s));
+        E->launches++;
+    }
     return CADM_OK;
 }
 
@@ -517,6 +519,7 @@ static int refit_common(Engine* E, int it, uint64_t seed, const float* z, cudaSt
     R.returns_log = E->returns_log + (size_t)it * m * c.candidates;
     R.elites_log = E->elites_log + (size_t)it * m * c.num_elites;
     R.mode_rs = 0; R.best = E->best;
+    R.ret_p = c.world == 1 ? E->ret_p : nullptr; R.p = c.particles;
     CU(E, launch_refit(R, s));
     E->launches++;
     return CADM_OK;

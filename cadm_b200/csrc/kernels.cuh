@@ -30,6 +30,9 @@ struct RefitParams {
     float* var;                     // [m, hA] in/out
     float* returns_log;             // nullable, [m, n_global] slot of this iteration
     int* elites_log;                // nullable, [m, k] slot of this iteration
+    const float* ret_p;             // nullable: [m, n_global, p] particle returns (world == 1: particle mean folded in)
+    int p;
+    int stage_elites;               // set by the launcher: elite rows fit in shared memory
     // random shooting (mode_rs): argmax only
     int mode_rs;
     int* best;                      // [m]
@@ -50,7 +53,7 @@ struct EncoderParams {
 
 cudaError_t launch_sample_actions(const SampleParams& S, cudaStream_t stream);
 cudaError_t launch_particle_mean(const float* ret_p, float* out, int count, int p, cudaStream_t stream);
-cudaError_t launch_refit(const RefitParams& R, cudaStream_t stream);
+cudaError_t launch_refit(RefitParams R, cudaStream_t stream);
 cudaError_t launch_rs_gather(const float* actions, const int* actions_int, const int* best, int m, int n_local, int h,
                              int A, float* action, int* action_int, cudaStream_t stream);
 cudaError_t launch_encoder(const EncoderParams& Q, cudaStream_t stream);

@@ -33,7 +33,7 @@ class PlannerModelBase:
     def _init_common(self, name, env, hidden_sizes, hidden_nonlinearity, output_nonlinearity, normalize_input,
                      n_forwards, n_candidates, ensemble_size, n_particles, use_cem, deterministic,
                      cp_hidden_sizes=(256, 128, 64), context_out_dim=10, history_length=10, state_diff=False,
-                     seed=0, m_max=32, precision="fp32", device=None, rank=0, world=1, context_layout="reference",
+                     seed=0, m_max=32, precision="tc3x", device=None, rank=0, world=1, context_layout="reference",
                      num_elites=50, cem_iters=5, alpha=0.1):
         if hidden_nonlinearity not in _ACTIVATIONS or output_nonlinearity not in _ACTIVATIONS:
             raise KeyError(hidden_nonlinearity)                      # the reference indexes _activations[...]

@@ -36,7 +36,7 @@ class PlannerConfig:
     num_elites: int = 50        # cadm/dynamics/core/utils.py:111
     cem_iters: int = 5          # :112
     alpha: float = 0.1          # :113
-    precision: str = "fp32"
+    precision: str = "tc3x"     # tensor cores, fp16 hi/lo split (parity mode); "fp32" = FFMA path
     rank: int = 0
     world: int = 1
     context_layout: str = "reference"
