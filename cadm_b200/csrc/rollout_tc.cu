@@ -41,7 +41,7 @@ constexpr int kXBytes = 2 * kMaxKB * kXChunkBytes;   // 53248 per operand half (
 constexpr int kMaxStageBytes = 2 * 208 * 32;   // hi + lo block of one K16 step, N = 208
 
 struct TcSmem {
-    size_t off_xhi, off_xlo, off_w, off_s, off_bias, off_vec, off_rowi, off_feat, off_act, off_ctx, off_bar, total;
+    size_t off_xhi, off_xlo, off_w, off_s, off_bias, off_vec, off_rowi, off_feat, off_zero, off_act, off_ctx, off_bar, total;
     int stages;
 };
 
@@ -56,7 +56,8 @@ __host__ __device__ inline TcSmem tc_smem_layout(int D, int A, int C, int n_hidd
     L.off_bias = o; o += (size_t)round_up(n_hidden * Np + NHp, 4) * 4;
     L.off_vec = o; o += (size_t)(2 * kMaxObs + 2 * kMaxAct + 5 * kMaxObs) * 4;
     L.off_rowi = o; o += (size_t)kTileRows * 6 * 4;
-    L.off_feat = o; o += (size_t)96 * 16;                       // layer-0 feature table (In <= 84, padded to 96)
+    L.off_feat = o; o += (size_t)96 * 16 + 96 * 8;              // layer-0 feature tables (In <= 84, padded to 96)
+    L.off_zero = o; o += 16;                                     // a zero word (padding features read it)
     L.off_act = o; o += (size_t)2 * kTileRows * A * 4;          // this step's / next step's actions of the tile rows
     L.off_ctx = o; o += (size_t)kTileRows * C * 4;              // context vector of every tile row
     o = (o + 15) / 16 * 16;
@@ -70,17 +71,25 @@ __host__ __device__ inline TcSmem tc_smem_layout(int D, int A, int C, int n_hidd
 // warp consumes them round-robin over the groups -- the order in which they become ready.  blk_of_pos / pos_of_blk map
 // between the natural block index kb and the position in that consumption order (also the order of the weight stream).
 __host__ __device__ inline int grp_first(int nkb, int g) { return (nkb * g + kEpiGroups - 1) / kEpiGroups; }
+__host__ __device__ inline int blk_group(int nkb, int kb) {
+    int g = 0;
+    while (g + 1 < kEpiGroups && kb >= grp_first(nkb, g + 1)) ++g;
+    return g;
+}
+// The epilogue groups are staggered by one block (group g starts when group g-1 has published its first block), so
+// block i of group g becomes ready at about time (g + i): consume in that order, ties by group.
+__host__ __device__ inline int blk_key(int nkb, int kb) {
+    const int g = blk_group(nkb, kb);
+    return (g + (kb - grp_first(nkb, g))) * 16 + g;
+}
 __host__ __device__ inline int blk_of_pos(int nkb, int pos) {
-    int round = 0, seen = 0;
-    for (;; ++round) {
-        for (int g = 0; g < kEpiGroups; ++g) {
-            const int kb = grp_first(nkb, g) + round;
-            if (kb < grp_first(nkb, g + 1)) {
-                if (seen == pos) return kb;
-                ++seen;
-            }
-        }
+    // the pos-th block in increasing key order (keys are distinct)
+    for (int kb = 0; kb < nkb; ++kb) {
+        int smaller = 0;
+        for (int o = 0; o < nkb; ++o) smaller += blk_key(nkb, o) < blk_key(nkb, kb) ? 1 : 0;
+        if (smaller == pos) return kb;
     }
+    return -1;
 }
 __host__ __device__ inline int pos_of_blk(int nkb, int kb) {
     for (int pos = 0; pos < nkb; ++pos)
@@ -189,7 +198,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
     float* bias = reinterpret_cast<float*>(smem + L.off_bias);
     float* vec = reinterpret_cast<float*>(smem + L.off_vec);
     int* rowi = reinterpret_cast<int*>(smem + L.off_rowi);
-    float4* feat = reinterpret_cast<float4*>(smem + L.off_feat);     // per layer-0 feature: {kind, index, mean, 1/(std+1e-10)}
+    int4* feat_i = reinterpret_cast<int4*>(smem + L.off_feat);        // per layer-0 feature: {byte offset, row stride, flags}
+    float2* feat_f = reinterpret_cast<float2*>(smem + L.off_feat + 96 * 16);   // {mean, 8 / (std + 1e-10)}
     float* act_s = reinterpret_cast<float*>(smem + L.off_act);
     float* ctx_s = reinterpret_cast<float*>(smem + L.off_ctx);
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
@@ -282,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                     const uint32_t b_lbo = (N >> 0) << 16;          // LBO = 16 N bytes -> (16 N) >> 4 = N, at bits [16, 30)
                     long long* dbg = (T.dbg && blockIdx.x == 0 && lane == 0 && tile == (int)blockIdx.x && t < 64 && g < 5)
                                          ? T.dbg + t * 64 + 32 + 4 * g : nullptr;
-                    long long xw = 0, ww = 0;
+                    long long xw = 0, ww = 0, iw = 0;
                     for (int pos = 0; pos < nkb; ++pos) {
                         const int kb = g == 0 ? T.order0[pos] : T.orderH[pos];
                         const long long c0 = dbg ? clock64() : 0;
@@ -291,7 +301,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                         if (dbg && pos == 0) dbg[0] = c1;
                         xphase ^= 1u << kb;
                         ptx::mbar_wait(&w_full[rc.stage], rc.phase);
-                        if (dbg) { xw += c1 - c0; ww += clock64() - c1; }
+                        const long long c2 = dbg ? clock64() : 0;
+                        if (dbg) { xw += c1 - c0; ww += c2 - c1; }
                         tc::fence_after_sync();
                         const uint32_t wb = w_a + rc.stage * kMaxStageBytes;
                         // descriptors: low word = addr >> 4 | LBO >> 4 << 16 ; high word = SBO >> 4 | version
@@ -311,12 +322,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                             }
                             tc::mma_commit(&w_empty[rc.stage]);
                         }
-                        __syncwarp();
+                        if (dbg) iw += clock64() - c2;
                         rc.advance();
                     }
                     if (ptx::elect_one()) tc::mma_commit(&acc_full[g_count & 1u]);
-                    __syncwarp();
-                    if (dbg) { dbg[1] = clock64(); dbg[2] = xw; dbg[3] = ww; }
+                    if (dbg) { dbg[1] = clock64(); dbg[2] = xw; dbg[3] = ww; T.dbg[t * 64 + 56 + g] = iw; }
                     ++g_count;
                 }
             }
@@ -344,30 +354,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
             v_minlv[i] = P.min_lv[i];
         }
 
-        // layer-0 feature table: kind 0 zero pad, 1 state element, 2 sin(state), 3 cos(state), 4 action (normalised),
-        // 5 action / one-hot (raw), 6 context
+        // layer-0 feature table (branch-free gather): feature k of row r reads the float at byte offset
+        //   x + r * y + (z & parity-of-step ? A-buffer stride : 0)      of shared memory,     then (v - mean) * inv8
+        // kinds: state element / action / context / zero word; sin, cos of the HalfCheetah angle are patched in by select
         for (int k = et; k < T.nkb0 * 16; k += kEpiThreads) {
-            float kind = 0.f, idx = 0.f, mean = 0.f, inv = 1.f;
+            int base = (int)L.off_zero, stride = 0, flags = 0;      // flags: 1 = action double buffer, 2 = sin, 4 = cos
+            float mean = 0.f, inv = 0.f;
             if (k < P.P) {
-                kind = 1.f; idx = (float)k;
+                int idx = k;
                 if (P.env_id == CADM_ENV_HALFCHEETAH) {          // [o1, sin o2, cos o2, o3:]
-                    if (k == 0) idx = 1.f;
-                    else if (k == 1) { kind = 2.f; idx = 2.f; }
-                    else if (k == 2) { kind = 3.f; idx = 2.f; }
+                    if (k == 0) idx = 1;
+                    else if (k == 1) { idx = 2; flags = 2; }
+                    else if (k == 2) { idx = 2; flags = 4; }
                 } else if (P.env_id == CADM_ENV_ANT) {
-                    idx = (float)(k + 1);                        // o[1:]
+                    idx = k + 1;                                  // o[1:]
                 }
+                base = (int)L.off_s + idx * 4; stride = (D + 1) * 4;
                 mean = P.obs_mean[k]; inv = 1.0f / (P.obs_std[k] + 1e-10f);
             } else if (k < P.P + A) {
                 const int ai = k - P.P;
-                idx = (float)ai;
-                if (P.discrete) kind = 5.f;
-                else { kind = 4.f; mean = P.act_mean[ai]; inv = 1.0f / (P.act_std[ai] + 1e-10f); }
+                base = (int)L.off_act + ai * 4; stride = A * 4; flags = 1;
+                if (P.discrete) { mean = 0.f; inv = 1.f; }
+                else { mean = P.act_mean[ai]; inv = 1.0f / (P.act_std[ai] + 1e-10f); }
             } else if (k < P.In) {
-                kind = 6.f; idx = (float)(k - P.P - A);
+                base = (int)L.off_ctx + (k - P.P - A) * 4; stride = P.C * 4; mean = 0.f; inv = 1.f;
             }
-            feat[k] = make_float4(kind, idx, mean, inv);
+            feat_i[k] = make_int4(base, stride, flags, 0);
+            feat_f[k] = make_float2(mean, inv * tc::kXScale);
         }
+        if (et == 0) *reinterpret_cast<float*>(smem + L.off_zero) = 0.f;
 
         for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
             const int e = tile / T.tiles_per_member;
@@ -445,19 +460,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                     float y[16];
                     float sn = 0.f, cs = 1.f;
                     if (P.env_id == CADM_ENV_HALFCHEETAH && kb == 0) sincosf(s[2], &sn, &cs);
-                    const int onehot = (P.discrete && P.row_mode == kRowsPlanner) ? __ldg(P.actions_int + (size_t)r_src[row] * P.h + t) : -1;
+                    const int par_off = (t & 1) * kTileRows * A * 4;
+                    if (P.discrete && P.row_mode == kRowsPlanner) {
+                        // one-hot of the integer action (random shooting with discrete actions): rare path, kept simple
+                        const int onehot = __ldg(P.actions_int + (size_t)r_src[row] * P.h + t);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float4 f = feat[kb * 16 + j];
-                        const int kind = (int)f.x, idx = (int)f.y;
-                        float src = 0.f;
-                        if (kind == 1) src = s[idx];
-                        else if (kind == 2) src = sn;
-                        else if (kind == 3) src = cs;
-                        else if (kind == 4) src = arow[idx];
-                        else if (kind == 5) src = onehot >= 0 ? (onehot == idx ? 1.f : 0.f) : arow[idx];
-                        else if (kind == 6) src = ctx_s[row * P.C + idx];
-                        y[j] = valid ? (src - f.z) * f.w * tc::kXScale : 0.f;
+                        for (int j = 0; j < 16; ++j) {
+                            const int k = kb * 16 + j;
+                            const int4 fi = feat_i[k];
+                            const float2 ff = feat_f[k];
+                            float src = *reinterpret_cast<const float*>(smem + fi.x + row * fi.y);
+                            if (fi.z & 1) src = (onehot == k - P.P) ? 1.f : 0.f;
+                            y[j] = valid ? (src - ff.x) * ff.y : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int4 fi = feat_i[kb * 16 + j];
+                            const float2 ff = feat_f[kb * 16 + j];
+                            float src = *reinterpret_cast<const float*>(smem + fi.x + row * fi.y + ((fi.z & 1) ? par_off : 0));
+                            src = (fi.z & 2) ? sn : src;
+                            src = (fi.z & 4) ? cs : src;
+                            y[j] = valid ? (src - ff.x) * ff.y : 0.f;
+                        }
                     }
                     if (dbg) dbg[15] = clock64();
                     store_block16(xhi, xlo, kb, row, y);
@@ -475,6 +500,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                     const uint32_t tcol = tmem_lane + buf * 256u;
                     const float* bl = bias + l * T.Np;
                     const int kb0 = grp_first(T.nkbH, group), kb1 = grp_first(T.nkbH, group + 1);
+                    // stagger the groups by one block: group g starts when group g-1 has published its first block, so the
+                    // MMA warp gets its first operand block ~3x sooner and the four warps of an SMSP run out of phase
+                    // (MUFU-heavy and FMA-heavy stretches overlap instead of colliding)
+                    if (group > 0) ptx::bar_sync(1 + group, 256);
+                    if (kb0 >= kb1 && group + 1 < kEpiGroups) ptx::bar_arrive(2 + group, 256);
                     uint32_t v[16];
                     if (kb0 < kb1) tc::tmem_ld16(tcol + kb0 * 16, v);
 #pragma unroll 1
@@ -492,6 +522,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                         store_block16(xhi, xlo, kb, row, y);
                         tc::fence_before_sync();
                         publish_block(&x_ready[kb], lane);
+                        if (kb == kb0 && group + 1 < kEpiGroups) ptx::bar_arrive(2 + group, 256);
                     }
                     if (dbg && l < 4) dbg[3 + 2 * l] = clock64();
                 }
@@ -520,35 +551,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                 if (dbg) dbg[11] = clock64();
 
                 // ---------- final epilogue: sample, next state ------------------------------------------
+                // thread = (row, quarter of the state dims): equal work for all 512 threads, independent chains per dim
                 {
                     const float* Hd = reinterpret_cast<const float*>(xhi);
-                    const int nblk = (D + 3) / 4;
-                    for (int item = et; item < kTileRows * nblk; item += kEpiThreads) {
-                        const int j = item / kTileRows, r = item - j * kTileRows;
-                        if (r >= nrows) continue;
-                        float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                    const int r = et & (kTileRows - 1);
+                    const int part = et >> 7;                                   // 0..3
+                    const int dper = (D + kEpiGroups - 1) / kEpiGroups;
+                    const int d0 = part * dper, d1 = min(D, d0 + dper);
+                    if (r < nrows && d0 < d1) {
+                        float nzv[16];                                          // normals of the Philox blocks covering [d0, d1)
+                        const int j0 = d0 >> 2, j1 = (d1 - 1) >> 2;             // at most 4 blocks (dper <= 12)
                         if (!P.deterministic) {
                             if (P.eps != nullptr) {
-                                const float* ep = P.eps + (P.row_mode == kRowsPlanner ? (size_t)t * eps_step_stride : 0) +
-                                                  (size_t)r_eps[r] * D + 4 * j;
+                                const float* ep = P.eps + (P.row_mode == kRowsPlanner ? (size_t)t * eps_step_stride : 0) + (size_t)r_eps[r] * D;
 #pragma unroll
-                                for (int i = 0; i < 4; ++i)
-                                    if (4 * j + i < D) nz[i] = __ldg(ep + i);
+                                for (int i = 0; i < 16; ++i) nzv[i] = (4 * j0 + i < D && 4 * j0 + i < d1) ? __ldg(ep + 4 * j0 + i) : 0.f;
                             } else {
-                                normal4_fast(P.seed, (uint32_t)j, (uint32_t)r_rid[r], (uint32_t)t, (uint32_t)P.it, nz);
+#pragma unroll
+                                for (int jb = 0; jb < 4; ++jb)
+                                    if (j0 + jb <= j1) normal4_fast(P.seed, (uint32_t)(j0 + jb), (uint32_t)r_rid[r], (uint32_t)t, (uint32_t)P.it, &nzv[4 * jb]);
                             }
                         }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int d = 4 * j + i;
-                            if (d >= D) break;
+                        for (int i = 0; i < 12; ++i) {
+                            const int d = d0 + i;
+                            if (d >= d1) break;
                             const float mu = Hd[d * kTileRows + r];
                             float lv = Hd[(D + d) * kTileRows + r];
                             const float dmu = mu * v_dscale[d] + v_dmean[d];
                             float delta = dmu;
                             if (!P.deterministic) {
                                 lv = fast_bounded_logvar(lv, v_maxlv[d], v_minlv[d]);
-                                delta = dmu + nz[i] * fast_exp((lv + v_2logstd[d]) * 0.5f);
+                                delta = dmu + nzv[d - 4 * j0] * fast_exp((lv + v_2logstd[d]) * 0.5f);
                             }
                             float* sp = S + r * (D + 1) + d;
                             const float sn = env_postproc(P.env_id, *sp, delta, d);
@@ -617,7 +651,7 @@ cudaError_t launch_rollout_tc(RolloutParams P, const unsigned char* wimg, long l
         if (e != cudaSuccess) return e;
         g_tc_smem = (int)L.total;
     }
-    if (name) *name = terms == 3 ? "rollout_tc_kernel(f16hi+bf16lo x3)" : "rollout_tc_kernel(f16 x1)";
+    if (name) *name = terms == 3 ? "rollout_tc_kernel(fp16 hi/lo x3)" : "rollout_tc_kernel(f16 x1)";
     const int grid = min(T.total_tiles, num_sms);
     rollout_tc_kernel<<<grid, kTcThreads, L.total, stream>>>(T);
     return cudaGetLastError();

@@ -22,4 +22,4 @@ for t in (1, 2, 15):
     print(f"step {t}: total {tr[t + 1, 0] - base if t + 1 < 30 else -1} cycles")
     print("  epi :", " ".join(f"{n}={tr[t, i] - base}" for i, n in enumerate(names)))
     print("  pro : prefetch=%d reward=%d built=%d" % (tr[t, 13] - base, tr[t, 14] - base, tr[t, 15] - base))
-    print("  mma :", " ".join(f"g{g}:first_ready={tr[t, 32 + 4 * g] - base},issued={tr[t, 33 + 4 * g] - base},xwait={tr[t, 34 + 4 * g]},wwait={tr[t, 35 + 4 * g]}" for g in range(5)))
+    print("  mma :", " ".join(f"g{g}:first_ready={tr[t, 32 + 4 * g] - base},issued={tr[t, 33 + 4 * g] - base},xwait={tr[t, 34 + 4 * g]},wwait={tr[t, 35 + 4 * g]},issue={tr[t, 56 + g]}" for g in range(5)))
