@@ -1,0 +1,21 @@
+"""Summarise an .ncu-rep (read here, no GPU needed): key metrics + stall breakdown -> CSV on stdout.
+usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x_summary.csv"""
+import csv
+import subprocess
+import sys
+
+KEEP = ("Kernel Name", "ID", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "sm__cycles_elapsed.max", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
+raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr = rows[0]
+idx = [i for i, h in enumerate(hdr) if h in KEEP or ("pcsamp_warps_issue_stalled" in h and "not_issued" not in h)]
+w = csv.writer(sys.stdout)
+for r in rows:
+    w.writerow([r[i] for i in idx])
