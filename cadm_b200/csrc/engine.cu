@@ -28,6 +28,10 @@ struct Engine {
     float* bpack = nullptr;
     // tensor-core image (hi/lo split, UMMA layout) and its 16-padded biases
     unsigned char* wimg = nullptr;
+    unsigned char* wimg_s = nullptr;   // same weights packed for the swapped-operand kernel (rollout_tcs.cu)
+    int tc_variant = 0;                // 0 auto, 1 row tiles (rollout_tc.cu), 2 swapped operands (rollout_tcs.cu)
+    int tcs_rows = 0;                  // rows per tile of the swapped kernel (0 = pick)
+    int tcs_kps = 2;                   // K16 blocks per weight stage the swapped image is packed with
     float* bpack_tc = nullptr;
     int Np16 = 0, NHp16 = 0, nkb0 = 0, nkbH = 0;
     long long wimg_member_stride = 0, bias_stride_tc = 0;
@@ -144,8 +148,19 @@ int run_rollout(Engine* E, RolloutParams& P, cudaStream_t s) {
         case CADM_PREC_TC_1X:
             P.bpack = E->bpack_tc;
             P.bias_stride = E->bias_stride_tc;
-            CU(E, launch_rollout_tc(P, E->wimg, E->wimg_member_stride, E->precision == CADM_PREC_TC_3X ? 3 : 1, E->num_sms, s,
-                                    &E->kernel_name, E->timing ? E->dbg : nullptr));
+            {
+                // small batches (fewer 128-row tiles than ~3/4 of the SMs) go to the swapped-operand kernel
+                const int tiles128 = P.E * ((P.rows_per_member + 127) / 128);
+                const bool swapped_ok = E->Np16 <= 256 && E->NHp16 <= 128;
+                const bool swapped = E->tc_variant == 2 || (E->tc_variant == 0 && swapped_ok && 4 * tiles128 < 3 * E->num_sms);
+                const int terms = E->precision == CADM_PREC_TC_3X ? 3 : 1;
+                if (swapped)
+                    CU(E, launch_rollout_tcs(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_kps, E->tcs_rows, E->num_sms, s,
+                                             &E->kernel_name, E->timing ? E->dbg : nullptr));
+                else
+                    CU(E, launch_rollout_tc(P, E->wimg, E->wimg_member_stride, terms, E->num_sms, s, &E->kernel_name,
+                                            E->timing ? E->dbg : nullptr));
+            }
             break;
         default:
             return fail(E, CADM_ERR_UNSUPPORTED, "unknown precision mode");
@@ -245,6 +260,7 @@ int cadm_plan_create(const CadmConfig* cfg, void** handle) {
     A(dalloc(E, &E->wpack, (size_t)c.ensemble * E->member_stride));
     A(dalloc(E, &E->bpack, (size_t)c.ensemble * E->bias_stride));
     A(dalloc(E, &E->wimg, (size_t)c.ensemble * E->wimg_member_stride));
+    A(dalloc(E, &E->wimg_s, (size_t)c.ensemble * E->wimg_member_stride));
     A(dalloc(E, &E->bpack_tc, (size_t)c.ensemble * E->bias_stride_tc));
     A(dalloc(E, &E->max_lv, c.obs_dim));
     A(dalloc(E, &E->min_lv, c.obs_dim));
@@ -329,6 +345,21 @@ int cadm_plan_set_weights(void* handle, const float* const* W, const float* cons
         CU(E, launch_pack_bias(E->bpack_tc, b[c.n_hidden], c.ensemble, c.obs_dim, 0, E->bias_stride_tc, tboff, s));
         CU(E, launch_pack_bias(E->bpack_tc, b[c.n_hidden + 1], c.ensemble, c.obs_dim, c.obs_dim, E->bias_stride_tc, tboff, s));
         E->launches += 4;
+    }
+    // the same image in the stage order / tiling of the swapped-operand kernel
+    {
+        long long toff = 0;
+        const int kps = E->tcs_kps;
+        for (int l = 0; l < c.n_hidden; ++l) {
+            const int in = l == 0 ? E->In : c.hidden;
+            const int nkb = l == 0 ? E->nkb0 : E->nkbH;
+            CU(E, launch_pack_tcs(E->wimg_s, W[l], c.ensemble, in, c.hidden, 0, nkb, E->Np16, kps, E->wimg_member_stride, toff, 1, s));
+            toff += (long long)nkb * E->Np16 * 64;
+            E->launches++;
+        }
+        CU(E, launch_pack_tcs(E->wimg_s, W[c.n_hidden], c.ensemble, c.hidden, c.obs_dim, 0, E->nkbH, E->NHp16, kps, E->wimg_member_stride, toff, 1, s));
+        CU(E, launch_pack_tcs(E->wimg_s, W[c.n_hidden + 1], c.ensemble, c.hidden, c.obs_dim, c.obs_dim, E->nkbH, E->NHp16, kps, E->wimg_member_stride, toff, 0, s));
+        E->launches += 2;
     }
     CU(E, cudaMemcpyAsync(E->max_lv, max_logvar, c.obs_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CU(E, cudaMemcpyAsync(E->min_lv, min_logvar, c.obs_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -662,14 +693,62 @@ int cadm_selftest_tc_gemm(const float* X, const float* W, int32_t K, int32_t N, 
     return CADM_OK;
 }
 
-int cadm_selftest_tc_rate(int32_t N, int32_t n_mma, int32_t a_lbo, int64_t* cycles_host) {
-    if (N < 16 || N > 208 || N % 16 || n_mma < 1 || !cycles_host) return fail(nullptr, CADM_ERR_ARG, "bad arguments");
+int cadm_set_option(void* handle, const char* name, int32_t value) {
+    Engine* E = H(handle);
+    if (!E || !name) return CADM_ERR_ARG;
+    const std::string k(name);
+    if (k == "tc_variant") {
+        if (value < 0 || value > 2) return fail(E, CADM_ERR_ARG, "tc_variant must be 0 (auto), 1 (row tiles) or 2 (swapped operands)");
+        E->tc_variant = value;
+    } else if (k == "tcs_rows") {
+        if (value < 0 || value > 64 || value % 16) return fail(E, CADM_ERR_ARG, "tcs_rows must be 0 (pick) or a multiple of 16 up to 64");
+        E->tcs_rows = value;
+    } else if (k == "tcs_kps") {
+        if (value < 1 || value > 4) return fail(E, CADM_ERR_ARG, "tcs_kps must be in 1..4");
+        if (E->have_weights) return fail(E, CADM_ERR_STATE, "tcs_kps must be set before cadm_plan_set_weights");
+        E->tcs_kps = value;
+    } else {
+        return fail(E, CADM_ERR_ARG, "unknown option: " + k);
+    }
+    return CADM_OK;
+}
+
+int cadm_selftest_tcs_gemm(const float* X, const float* W, int32_t rows, int32_t K, int32_t N, int32_t kps, int32_t terms,
+                           float* out, void* stream) {
+    if (!X || !W || !out || rows < 16 || rows > 64 || rows % 16 || K < 1 || K > 208 || N < 1 || N > 256 || kps < 1 || kps > 4 ||
+        (terms != 1 && terms != 3))
+        return fail(nullptr, CADM_ERR_ARG, "selftest: need rows in {16,32,48,64}, 1 <= K <= 208, 1 <= N <= 256, kps 1..4, terms 1 or 3");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nkb = (K + 15) / 16;
+    const int Npad = round_up(N, 16);
+    unsigned char* img = nullptr;
+    const size_t bytes = (size_t)nkb * Npad * 64;
+    cudaError_t e = cudaMalloc(&img, bytes);
+    if (e != cudaSuccess) return fail(nullptr, CADM_ERR_CUDA, cudaGetErrorString(e));
+    e = launch_pack_tcs(img, W, 1, K, N, 0, nkb, Npad, kps, (long long)bytes, 0, 1, s);
+    if (e == cudaSuccess) e = launch_tcs_gemm_selftest(X, img, rows, K, N, kps, terms, out, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(img);
+    if (e != cudaSuccess) return fail(nullptr, CADM_ERR_CUDA, cudaGetErrorString(e));
+    return CADM_OK;
+}
+
+int cadm_selftest_tc_rate(int32_t N, int32_t n_mma, int32_t a_lbo, int32_t n_acc, int32_t swapped, int32_t background,
+                          int64_t* cycles_host) {
+    if (N < 16 || N > 208 || N % 16 || n_mma < 1 || !cycles_host || n_acc < 1 || n_acc > 8 || (n_acc & (n_acc - 1)) ||
+        (512 / n_acc) < N)
+        return fail(nullptr, CADM_ERR_ARG, "bad arguments");
     long long* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, 2 * sizeof(long long));
-    if (e == cudaSuccess) e = launch_tc_mma_rate(N, n_mma, a_lbo, d, 0);
+    unsigned char* src = nullptr;
+    cudaError_t e = cudaMalloc(&d, 4 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&src, 1 << 20);
+    if (e == cudaSuccess) e = cudaMemset(src, 0x3c, 1 << 20);
+    if (e == cudaSuccess) e = cudaMemset(d, 0, 4 * sizeof(long long));
+    if (e == cudaSuccess) e = launch_tc_mma_rate(N, n_mma, a_lbo, n_acc, swapped, background, src, d, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 3 * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(d);
+    cudaFree(src);
     if (e != cudaSuccess) return fail(nullptr, CADM_ERR_CUDA, cudaGetErrorString(e));
     return CADM_OK;
 }

@@ -750,21 +750,27 @@ cudaError_t launch_tc_gemm_selftest(const float* X, const unsigned char* wimg, i
 
 // ------------------------------------------------------------------------------------------------
 // Micro-benchmark: `n_mma` back-to-back tcgen05.mma (M = 128, N, K = 16, kind::f16) on resident shared-memory operands
-// in the rollout kernel's layouts, nothing else running on the SM.  Reports clock64 cycles (issue of first -> commit seen).
+// in the rollout kernels' layouts, nothing else running on the SM.  `n_acc` accumulators are used round-robin (1 = every
+// MMA depends on the previous one); `swapped` selects the operand layouts of rollout_tcs.cu (A = 128 weight rows K-major,
+// B = N batch rows MN-major).  Reports clock64 cycles (issue of first -> commit seen).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int N, int n_mma, int a_lbo, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int N, int n_mma, int a_lbo, int n_acc, int swapped, int bg, const unsigned char* bg_src,
+                                                              long long* cycles) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kXBytes + kMaxStageBytes);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kXBytes + 65536);      // [0] MMA done, [1] stop flag, [2..5] bg copies
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    volatile uint32_t* stop = reinterpret_cast<volatile uint32_t*>(bars + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < (2 * kXBytes + kMaxStageBytes) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // 1.0h
+    for (int i = tid; i < (2 * kXBytes + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // 1.0h
     if (tid == 0) {
         ptx::mbar_init(&bars[0], 1);
+        for (int i = 2; i < 6; ++i) ptx::mbar_init(&bars[i], 1);
+        *stop = 0u;
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
         __syncwarp();
-        tc::tmem_alloc(tmem_slot, 256);
+        tc::tmem_alloc(tmem_slot, 512);
         tc::tmem_relinquish();
     }
     ptx::fence_proxy_async();
@@ -772,36 +778,100 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int N, int n_mma, i
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    if (tid == 0) {
+    if (warp == 0) {
         const uint32_t x_a = ptx::smem_u32(smem), w_a = ptx::smem_u32(smem + 2 * kXBytes);
-        const uint32_t idesc = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
+        const uint32_t idesc = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N) | (swapped ? (1u << 16) : 0u);
+        const uint32_t acc_stride = 512u / (uint32_t)n_acc;
+        const int style = a_lbo >> 16;           // issue-loop style (diagnostic): 0 = elect per MMA, 1 = one elected region
+        a_lbo &= 0xffff;
         const long long t0 = clock64();
-        for (int i = 0; i < n_mma; ++i) {
-            const int kb = i % kMaxKB;
-            const uint64_t a = tc::smem_desc(x_a + 2 * kb * kXChunkBytes, a_lbo, 128);
-            const uint64_t b = tc::smem_desc(w_a, 16 * N, 128);
-            tc::mma_f16_ss(tmem_base, a, b, idesc, i > 0 ? 1u : 0u);
+        if (style == 0) {
+            // the whole warp walks the loop with warp-uniform operands; one elected lane issues each MMA
+            for (int i = 0; i < n_mma; ++i) {
+                const int kb = i % kMaxKB;
+                uint64_t a, b;
+                if (swapped) {
+                    a = tc::smem_desc(w_a + (kb & 1) * 4096, 2048, 128);            // 128 weight rows, K-major
+                    b = tc::smem_desc(x_a + kb * 256, 128, 3328);                    // N batch rows, MN-major
+                } else {
+                    a = tc::smem_desc(x_a + 2 * kb * kXChunkBytes, a_lbo, 128);
+                    b = tc::smem_desc(w_a, 16 * N, 128);
+                }
+                if (ptx::elect_one()) tc::mma_f16_ss(tmem_base + (uint32_t)(i % n_acc) * acc_stride, a, b, idesc, i >= n_acc ? 1u : 0u);
+                __syncwarp();
+            }
+        } else if (ptx::elect_one()) {
+            // one elected thread runs the whole loop: groups of 3 MMAs (the hi/lo terms of one K16 block), descriptors
+            // advanced by constant adds, 13 K blocks per accumulator pass
+            const uint64_t a0 = swapped ? tc::smem_desc(w_a, 2048, 128) : tc::smem_desc(x_a, a_lbo, 128);
+            const uint64_t b0 = swapped ? tc::smem_desc(x_a, 128, 3328) : tc::smem_desc(w_a, 16 * N, 128);
+            const uint64_t a_inc = swapped ? (256u >> 4) : ((2u * kXChunkBytes) >> 4);
+            const uint64_t b_inc = swapped ? (256u >> 4) : 0u;
+            const uint64_t lo_off = 8192u >> 4;
+            int issued = 0, pass = 0;
+            while (issued < n_mma) {
+                const uint32_t d = tmem_base + (uint32_t)(pass % n_acc) * acc_stride;
+                uint64_t a = a0, b = b0;
+#pragma unroll
+                for (int kb = 0; kb < kMaxKB; ++kb) {
+                    tc::mma_f16_ss(d, a, b, idesc, (kb > 0 || pass >= n_acc) ? 1u : 0u);
+                    tc::mma_f16_ss(d, a, b + lo_off, idesc, 1u);
+                    tc::mma_f16_ss(d, a + lo_off, b, idesc, 1u);
+                    a += a_inc;
+                    b += b_inc;
+                    if ((bg & 2) && (kb & 1)) tc::mma_commit(&bars[5]);       // a commit every 6 MMAs, like a weight stage
+                }
+                issued += 3 * kMaxKB;
+                ++pass;
+            }
         }
+        __syncwarp();
         const long long t1 = clock64();
-        tc::mma_commit(&bars[0]);
+        if (ptx::elect_one()) tc::mma_commit(&bars[0]);
+        __syncwarp();
         ptx::mbar_wait(&bars[0], 0);
         const long long t2 = clock64();
-        cycles[0] = t1 - t0;
-        cycles[1] = t2 - t0;
+        if (tid == 0) {
+            cycles[0] = t1 - t0;
+            cycles[1] = t2 - t0;
+            *stop = 1u;
+        }
+    } else if (warp == 2 && (bg & 1)) {
+        // background weight stream: 8 KB bulk copies global -> shared (4 in flight) into a region the MMAs do not read
+        if (tid == 64) {
+            unsigned char* dst = smem + 2 * kXBytes + 32768;
+            uint32_t ph[4] = {0u, 0u, 0u, 0u};
+            long long n = 0;
+            for (int i = 0; i < 4; ++i) {
+                ptx::mbar_arrive_expect_tx(&bars[2 + i], 8192);
+                ptx::bulk_g2s(dst + i * 8192, bg_src + ((n++ * 8192) & 0xfffff), 8192, &bars[2 + i]);
+            }
+            while (!*stop) {
+                for (int i = 0; i < 4; ++i) {
+                    ptx::mbar_wait(&bars[2 + i], ph[i]);
+                    ph[i] ^= 1u;
+                    ptx::mbar_arrive_expect_tx(&bars[2 + i], 8192);
+                    ptx::bulk_g2s(dst + i * 8192, bg_src + ((n++ * 8192) & 0xfffff), 8192, &bars[2 + i]);
+                }
+            }
+            for (int i = 0; i < 4; ++i) ptx::mbar_wait(&bars[2 + i], ph[i]);
+            cycles[2] = n;
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 1) {
         __syncwarp();
-        tc::tmem_dealloc(tmem_base, 256);
+        tc::tmem_dealloc(tmem_base, 512);
     }
 }
 
-cudaError_t launch_tc_mma_rate(int N, int n_mma, int a_lbo, long long* cycles, cudaStream_t stream) {
-    const int smem_bytes = 2 * kXBytes + kMaxStageBytes + 64;
+cudaError_t launch_tc_mma_rate(int N, int n_mma, int a_lbo, int n_acc, int swapped, int bg, const unsigned char* bg_src,
+                               long long* cycles, cudaStream_t stream) {
+    const int smem_bytes = 2 * kXBytes + 65536 + 128;
     cudaError_t e = cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
-    tc_mma_rate_kernel<<<1, 128, smem_bytes, stream>>>(N, n_mma, a_lbo, cycles);
+    tc_mma_rate_kernel<<<1, 128, smem_bytes, stream>>>(N, n_mma, a_lbo, n_acc, swapped, bg, bg_src, cycles);
     return cudaGetLastError();
 }
 

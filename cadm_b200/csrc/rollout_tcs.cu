@@ -1,0 +1,800 @@
+// Persistent tensor-core rollout kernel, SWAPPED operands ("small-tile" variant of rollout_tc.cu).
+//
+// The planner's batch is small: HalfCheetah PE-TS has 800 rows per ensemble member, i.e. 35 tiles of 128 rows for a
+// 148-SM part.  This variant puts the HIDDEN UNITS on the MMA's M axis and the rows on its N axis,
+//
+//      D^T[hidden (TMEM lanes) x rows (TMEM columns)] = W^T[hidden x K] * X^T[K x rows],
+//
+// so a CTA can own as few as 16 rows and the tile count follows the SM count (C2: 85 CTAs x 48 rows or 125 x 32).
+//   A operand  = weights, K-major no-swizzle core matrices (the layout the weight image is packed in); hidden widths
+//                above 128 use two M = 128 tiles (the second one reads past its 80 rows into finite weight bytes; those
+//                accumulator lanes are never read back)
+//   B operand  = activations, MN-major (row index contiguous) no-swizzle core matrices: an epilogue thread owns ONE
+//                hidden unit (TMEM lane) and writes 8 consecutive rows as one 16-byte store
+//   precision  = fp16 hi/lo split x3 into one fp32 accumulator, exactly as rollout_tc.cu (same scales, same terms)
+//
+// Warp roles (576 threads): warp 0 streams the member's weight image from L2 through a shared-memory ring (1-D bulk
+// async copies, one stage = up to `kps` K16 blocks of one M tile, hi + lo); warp 1 issues the MMAs (elect.sync);
+// warps 2-9 are the epilogue of M tile 0, warps 10-17 of M tile 1 (quarter = TMEM lane quarter, two column slices
+// each).  The MMAs of M tile 1 run while tile 0's epilogue computes; tile 0 defers its shared-memory stores until tile
+// 1's MMAs (which still read the layer input) have completed, and the next layer's first K blocks start while tile 1's
+// epilogue runs: the tensor pipe stays busy inside one dependent layer chain.
+// Everything else (prologue gather / normalise / reward, bounded logvar, Gaussian sample, obs_postproc --
+// cadm/dynamics/core/utils.py:141-168) matches rollout_tc.cu, re-indexed for rows-as-columns.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include "rng.cuh"
+
+namespace cadm {
+
+constexpr int kSEpiThreads = 512;
+constexpr int kSThreads = 64 + kSEpiThreads;
+constexpr int kSMaxRows = 64;                  // rows per tile (multiple of 16)
+constexpr int kSAccCols = 64;                  // TMEM columns reserved per accumulator (buffer, M tile)
+constexpr int kSMaxStages = 16;
+constexpr int kSMaxKps = 4;
+
+struct TcsSmem {
+    size_t off_xhi, off_xlo, off_w, off_s, off_hd, off_bias, off_vec, off_rowi, off_feat, off_zero, off_act, off_ctx, off_bar, total;
+    int xbytes, slot_bytes;
+};
+
+__host__ __device__ inline TcsSmem tcs_smem_layout(int N, int D, int A, int C, int n_hidden, int Np, int NHp, int Kcap, int kps,
+                                                   int stages) {
+    TcsSmem L;
+    size_t o = 0;
+    L.xbytes = (N / 8) * (Kcap / 8) * 128;
+    L.slot_bytes = kps * 8192;
+    L.off_xhi = o; o += L.xbytes;
+    L.off_xlo = o; o += L.xbytes;
+    o = (o + 127) / 128 * 128;
+    L.off_w = o; o += (size_t)stages * L.slot_bytes;
+    L.off_s = o; o += (size_t)round_up(N * (D + 1), 4) * 4;
+    L.off_hd = o; o += (size_t)NHp * N * 4;
+    o = (o + 15) / 16 * 16;
+    L.off_bias = o; o += (size_t)round_up(n_hidden * Np + NHp, 4) * 4;
+    L.off_vec = o; o += (size_t)(2 * kMaxObs + 2 * kMaxAct + 5 * kMaxObs) * 4;
+    L.off_rowi = o; o += (size_t)N * 6 * 4;
+    L.off_feat = o; o += (size_t)96 * 16 + 96 * 8;
+    L.off_zero = o; o += 16;
+    L.off_act = o; o += (size_t)2 * N * A * 4;
+    L.off_ctx = o; o += (size_t)N * (C > 0 ? C : 1) * 4;
+    o = (o + 15) / 16 * 16;
+    L.off_bar = o; o += (size_t)(2 * kSMaxStages + 2 + 4 + 2) * 8;   // w_full, w_empty, xr[2], acc_full[4], tmem slot
+    L.total = o;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight image: per member, per GEMM, per M tile (rows R = min(128, Npad - 128 mt)), per stage of `kps` K16 blocks:
+//   [hi: (2 kbs) k-chunks x (R rows x 16 B)] [lo: same]        byte(row, chunk c, kk) = c 16 R + 16 row + 2 (kk % 8)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_tcs_kernel(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad,
+                                int kps, long long member_stride, long long layer_off, int clear, float wscale) {
+    const long long per_member = (long long)nkb * 16 * Npad;
+    const long long total = (long long)E * per_member;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i / per_member);
+        long long r = i - (long long)e * per_member;
+        const int n = (int)(r / (nkb * 16));
+        const int k = (int)(r - (long long)n * (nkb * 16));
+        const int ns = n - col0;
+        const bool valid = ns >= 0 && ns < out && k < in;
+        if (!valid && !clear) continue;
+        const float w = valid ? src[((size_t)e * in + k) * out + ns] * wscale : 0.f;
+        uint32_t hi, lo;
+        tc::split2(w, 0.f, hi, lo);
+        const int mt = n >> 7, row = n & 127;
+        const int R = min(128, Npad - 128 * mt);
+        const int kb = k >> 4, kk = k & 15;
+        const int s0 = (kb / kps) * kps;
+        const int kbs = min(kps, nkb - s0);
+        const int c = 2 * (kb - s0) + (kk >> 3);
+        const long long off = (mt ? (long long)nkb * 64 * 128 : 0) + (long long)s0 * 64 * R + (long long)c * 16 * R + 16 * row + 2 * (kk & 7);
+        unsigned char* base = dst + e * member_stride + layer_off;
+        *reinterpret_cast<unsigned short*>(base + off) = (unsigned short)(hi & 0xffffu);
+        *reinterpret_cast<unsigned short*>(base + off + (long long)kbs * 32 * R) = (unsigned short)(lo & 0xffffu);
+    }
+}
+
+cudaError_t launch_pack_tcs(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad, int kps,
+                            long long member_stride, long long layer_off, int clear, cudaStream_t stream) {
+    const long long total = (long long)E * nkb * 16 * Npad;
+    pack_tcs_kernel<<<(int)min((total + 255) / 256, (long long)2368), 256, 0, stream>>>(dst, src, E, in, out, col0, nkb, Npad, kps,
+                                                                                        member_stride, layer_off, clear, tc::kWScale);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace tcs {
+
+// instruction descriptor: kind::f16, fp32 accumulate, A K-major, B MN-major (bit 16), M = 128, N = rows
+__host__ __device__ constexpr uint32_t idesc(uint32_t rows) {
+    return (1u << 4) | (tc::kFmtF16 << 7) | (tc::kFmtF16 << 10) | (1u << 16) | ((rows >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+struct Ring {
+    int stage;
+    uint32_t phase;
+    int n;
+    __device__ __forceinline__ void advance() {
+        if (++stage == n) { stage = 0; phase ^= 1u; }
+    }
+};
+
+// 8 consecutive rows of one feature / hidden unit k -> one 16-byte store per operand half (MN-major core matrix row)
+__device__ __forceinline__ void store_rows8(unsigned char* xhi, unsigned char* xlo, int xsbo, int rgroup, int k, const float (&y)[8]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tc::split2(y[2 * j], y[2 * j + 1], h[j], l[j]);
+    const int o = rgroup * xsbo + (k >> 3) * 128 + (k & 7) * 16;
+    *reinterpret_cast<uint4*>(xhi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(xlo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// the MMAs of one weight stage: kbs K16 blocks x `terms` products into d_tmem
+__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t slot_addr, int R, int kbs, int kb0, uint32_t xhi_a,
+                                            uint32_t xlo_a, uint32_t xsbo, uint32_t idesc_v, int terms) {
+    const uint32_t hi32 = (1u << 14);                                   // descriptor version 1 (bit 46)
+    const uint32_t a_hi32 = hi32 | (128u >> 4);                         // A: SBO = 128 B between 8-row groups
+    const uint32_t b_hi32 = hi32 | (xsbo >> 4);                         // B: SBO = stride between 8-row (N) groups
+    const uint32_t a_lbo = ((uint32_t)(16 * R) >> 4) << 16;             // A: LBO = stride between the two k-chunks
+    const uint32_t b_lbo = (128u >> 4) << 16;                           // B: LBO = stride between the two k-groups
+    const uint32_t lo_off = (uint32_t)kbs * 32u * (uint32_t)R;
+    for (int j = 0; j < kbs; ++j) {
+        const int kb = kb0 + j;
+        const uint32_t wa = slot_addr + (uint32_t)(2 * j) * 16u * (uint32_t)R;
+        const uint64_t a_hi = ((uint64_t)a_hi32 << 32) | ((wa >> 4) | a_lbo);
+        const uint64_t a_lo = ((uint64_t)a_hi32 << 32) | (((wa + lo_off) >> 4) | a_lbo);
+        const uint64_t b_hi = ((uint64_t)b_hi32 << 32) | (((xhi_a + kb * 256u) >> 4) | b_lbo);
+        const uint64_t b_lo = ((uint64_t)b_hi32 << 32) | (((xlo_a + kb * 256u) >> 4) | b_lbo);
+        tc::mma_f16_ss(d_tmem, a_hi, b_hi, idesc_v, kb > 0 ? 1u : 0u);
+        if (terms == 3) {
+            tc::mma_f16_ss(d_tmem, a_hi, b_lo, idesc_v, 1u);            // W_hi X_lo
+            tc::mma_f16_ss(d_tmem, a_lo, b_hi, idesc_v, 1u);            // W_lo X_hi
+        }
+    }
+}
+
+}  // namespace tcs
+
+struct TcsParams {
+    RolloutParams R;
+    const unsigned char* wimg;
+    long long wimg_member_stride;
+    int Np, NHp, nkb0, nkbH, Kcap;
+    int terms, stages, kps;
+    int N;                       // rows per tile (multiple of 16, <= kSMaxRows)
+    int nmt;                     // M tiles of a hidden GEMM: 1 (Np <= 128) or 2
+    int tiles_per_member, total_tiles;
+    long long* dbg;              // nullable: clock64 trace of CTA 0, [step][64]
+};
+
+__global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_constant__ TcsParams T) {
+    const RolloutParams& P = T.R;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int N = T.N;
+    const TcsSmem L = tcs_smem_layout(N, P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, T.Kcap, T.kps, T.stages);
+    unsigned char* xhi = smem + L.off_xhi;
+    unsigned char* xlo = smem + L.off_xlo;
+    unsigned char* wring = smem + L.off_w;
+    float* S = reinterpret_cast<float*>(smem + L.off_s);
+    float* Hd = reinterpret_cast<float*>(smem + L.off_hd);             // [NHp][N] head outputs
+    float* bias = reinterpret_cast<float*>(smem + L.off_bias);
+    float* vec = reinterpret_cast<float*>(smem + L.off_vec);
+    int* rowi = reinterpret_cast<int*>(smem + L.off_rowi);
+    int4* feat_i = reinterpret_cast<int4*>(smem + L.off_feat);
+    float2* feat_f = reinterpret_cast<float2*>(smem + L.off_feat + 96 * 16);
+    float* act_s = reinterpret_cast<float*>(smem + L.off_act);
+    float* ctx_s = reinterpret_cast<float*>(smem + L.off_ctx);
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    uint64_t* w_empty = w_full + kSMaxStages;
+    uint64_t* xr = w_empty + kSMaxStages;          // [2]: layer input produced by the M-tile-0 / M-tile-1 warps
+    uint64_t* acc_full = xr + 2;                   // [buffer][M tile]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 4);
+
+    float* v_dmean = vec + 2 * kMaxObs + 2 * kMaxAct;
+    float* v_dscale = v_dmean + kMaxObs;
+    float* v_2logstd = v_dscale + kMaxObs;
+    float* v_maxlv = v_2logstd + kMaxObs;
+    float* v_minlv = v_maxlv + kMaxObs;
+    int* r_mi = rowi;
+    int* r_src = rowi + N;
+    int* r_pi = rowi + 2 * N;
+    int* r_ctx = rowi + 3 * N;
+    int* r_rid = rowi + 4 * N;
+    int* r_eps = rowi + 5 * N;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nstage = T.stages;
+    const int gemms_per_step = P.n_hidden + 1;
+    const int xsbo = (T.Kcap / 8) * 128;
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
+        ptx::mbar_init(&xr[0], 8);
+        ptx::mbar_init(&xr[1], 8);
+        for (int i = 0; i < 4; ++i) ptx::mbar_init(&acc_full[i], 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_alloc(tmem_slot, 4 * kSAccCols);
+        tc::tmem_relinquish();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ======================= warp 0: weight producer =============================================
+    if (warp == 0) {
+        if (lane == 0) {
+            tcs::Ring rp{0, 0, nstage};
+            for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
+                const int e = tile / T.tiles_per_member;
+                const unsigned char* wsrc = T.wimg + (size_t)e * T.wimg_member_stride;
+                for (int t = 0; t < P.h; ++t) {
+                    size_t off = 0;
+                    for (int g = 0; g < gemms_per_step; ++g) {
+                        const int nkb = g == 0 ? T.nkb0 : T.nkbH;
+                        const int Npad = g == P.n_hidden ? T.NHp : T.Np;
+                        const int nmt = (Npad + 127) >> 7;
+                        for (int mt = 0; mt < nmt; ++mt) {
+                            const int R = min(128, Npad - 128 * mt);
+                            for (int s0 = 0; s0 < nkb; s0 += T.kps) {
+                                const uint32_t bytes = (uint32_t)min(T.kps, nkb - s0) * 64u * (uint32_t)R;
+                                ptx::mbar_wait(&w_empty[rp.stage], rp.phase ^ 1u);
+                                ptx::mbar_arrive_expect_tx(&w_full[rp.stage], bytes);
+                                ptx::bulk_g2s(wring + (size_t)rp.stage * L.slot_bytes, wsrc + off, bytes, &w_full[rp.stage]);
+                                off += bytes;
+                                rp.advance();
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // ======================= warp 1: MMA issuer ==================================================
+    // ONE elected thread runs the whole MMA schedule (waits included): inside an elect.sync region ptxas keeps the
+    // descriptors in uniform registers and the UTCHMMAs issue back to back -- measured 40 cycles per MMA at N = 32..64
+    // (the shared-memory operand fetch: 4 KB of A per MMA), against ~100 when every MMA is elected separately.
+    else if (warp == 1) {
+        if (ptx::elect_one()) {
+            tcs::Ring rc{0, 0, nstage};
+            uint32_t g_count = 0;
+            const uint32_t xhi_d = ptx::smem_u32(xhi) >> 4, xlo_d = ptx::smem_u32(xlo) >> 4, w_a = ptx::smem_u32(wring);
+            const uint32_t idesc_v = tcs::idesc((uint32_t)N);
+            const uint32_t hi32 = (1u << 14);                                   // descriptor version 1 (bit 46)
+            const uint64_t a_top = (uint64_t)(hi32 | (128u >> 4)) << 32;        // A: SBO = 128 B between 8-row groups
+            const uint64_t b_top = (uint64_t)(hi32 | ((uint32_t)xsbo >> 4)) << 32;   // B: SBO = stride between 8-row (N) groups
+            const uint32_t b_lbo = (128u >> 4) << 16;                           // B: LBO = stride between the two k-groups
+            for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
+                for (int t = 0; t < P.h; ++t) {
+                    for (int g = 0; g < gemms_per_step; ++g) {
+                        const int nkb = g == 0 ? T.nkb0 : T.nkbH;
+                        const int Npad = g == P.n_hidden ? T.NHp : T.Np;
+                        const int nmt = (Npad + 127) >> 7;
+                        const uint32_t buf = g_count & 1u;
+                        const uint32_t xpar = g_count & 1u;
+                        // K blocks [0, kb_split) come from the M-tile-0 warps of the producing phase, the rest from tile 1
+                        // (the prologue spreads layer 0 over all warps: wait for both up front)
+                        const int kb_split = (g == 0 || T.nmt == 1) ? 0 : 8;
+                        bool waited1 = false;
+                        long long* dbg = (T.dbg && blockIdx.x == 0 && tile == (int)blockIdx.x && t < 64 && g < 5)
+                                             ? T.dbg + t * 64 + 32 + 4 * g : nullptr;
+                        long long xw = 0, ww = 0;
+                        for (int mt = 0; mt < nmt; ++mt) {
+                            const uint32_t R = (uint32_t)min(128, Npad - 128 * mt);
+                            const uint32_t d_tmem = tmem_base + (buf * 2u + (uint32_t)mt) * kSAccCols;
+                            const uint32_t a_lbo = R << 16;                     // A: LBO = 16 R bytes between the two k-chunks
+                            for (int s0 = 0; s0 < nkb; s0 += T.kps) {
+                                const int kbs = min(T.kps, nkb - s0);
+                                const long long c0 = dbg ? clock64() : 0;
+                                if (mt == 0 && s0 == 0) ptx::mbar_wait(&xr[0], xpar);
+                                const bool last_stage = mt == nmt - 1 && s0 + kbs >= nkb;
+                                if (!waited1 && (s0 + kbs > kb_split || last_stage)) { ptx::mbar_wait(&xr[1], xpar); waited1 = true; }
+                                const long long c1 = dbg ? clock64() : 0;
+                                if (dbg && mt == 0 && s0 == 0) dbg[0] = c1;
+                                ptx::mbar_wait(&w_full[rc.stage], rc.phase);
+                                const long long c2 = dbg ? clock64() : 0;
+                                if (dbg) { xw += c1 - c0; ww += c2 - c1; }
+                                tc::fence_after_sync();
+                                const uint32_t slot = w_a + rc.stage * L.slot_bytes;
+                                uint32_t wa_hi = (slot >> 4) | a_lbo;                              // W_hi of the stage's first K block
+                                uint32_t wa_lo = ((slot + (uint32_t)kbs * 32u * R) >> 4) | a_lbo;  // W_lo
+                                uint32_t xb_hi = (xhi_d + (uint32_t)s0 * 16u) | b_lbo;             // X_hi (256 B per K block)
+                                uint32_t xb_lo = (xlo_d + (uint32_t)s0 * 16u) | b_lbo;
+                                uint32_t accum = s0 > 0 ? 1u : 0u;
+                                for (int j = 0; j < kbs; ++j) {
+                                    tc::mma_f16_ss(d_tmem, a_top | wa_hi, b_top | xb_hi, idesc_v, accum);
+                                    if (T.terms == 3) {
+                                        tc::mma_f16_ss(d_tmem, a_top | wa_hi, b_top | xb_lo, idesc_v, 1u);      // W_hi X_lo
+                                        tc::mma_f16_ss(d_tmem, a_top | wa_lo, b_top | xb_hi, idesc_v, 1u);      // W_lo X_hi
+                                    }
+                                    accum = 1u;
+                                    wa_hi += 2u * R; wa_lo += 2u * R;                // two k-chunks of R rows x 16 B, in 16-B units
+                                    xb_hi += 16u; xb_lo += 16u;
+                                }
+                                tc::mma_commit(&w_empty[rc.stage]);
+                                rc.advance();
+                            }
+                            tc::mma_commit(&acc_full[buf * 2u + (uint32_t)mt]);
+                        }
+                        if (dbg) { dbg[1] = clock64(); dbg[2] = xw; dbg[3] = ww; }
+                        ++g_count;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // ======================= warps 2..17: prologue / epilogue ======================================
+    else {
+        const int et = tid - 64;                       // 0..511
+        const int ew = warp - 2;                       // 0..15
+        const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+        const int mtg = ew >> 3;                       // M tile this warp serves
+        const int cslice = (ew >> 2) & 1;              // column (row-of-the-batch) half
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int jh = mtg * 128 + quarter * 32 + lane;                 // hidden unit (TMEM lane of M tile mtg)
+        const int nch = N >> 4;                        // 8-column chunks per column slice (N / 2 / 8)
+        const int col0 = cslice * (N >> 1);
+        uint32_t g_count = 0;
+        uint32_t c1cnt[2] = {0u, 0u};                  // completions of acc_full[buf][1] so far
+        const int D = P.D, A = P.A;
+        const size_t eps_step_stride = (size_t)P.E * P.q * P.m * P.n_global * D;
+        const int nj = (D + 3) >> 2;                   // Philox blocks (4 state dims each) per row
+
+        for (int i = et; i < D; i += kSEpiThreads) {
+            v_dmean[i] = P.delta_mean[i];
+            v_dscale[i] = P.delta_std[i] + 1e-10f;
+            v_2logstd[i] = 2.0f * logf(P.delta_std[i]);
+            v_maxlv[i] = P.max_lv[i];
+            v_minlv[i] = P.min_lv[i];
+        }
+        // layer-0 feature table: feature k of row r reads the float at smem byte offset x + r * y (+ action double-buffer
+        // offset when z & 1), then (v - mean) * (8 / (std + 1e-10)); sin / cos of the HalfCheetah angle by select
+        const int K0 = T.nkb0 * 16;
+        for (int k = et; k < K0; k += kSEpiThreads) {
+            int base = (int)L.off_zero, stride = 0, flags = 0;
+            float mean = 0.f, inv = 0.f;
+            if (k < P.P) {
+                int idx = k;
+                if (P.env_id == CADM_ENV_HALFCHEETAH) {          // [o1, sin o2, cos o2, o3:]
+                    if (k == 0) idx = 1;
+                    else if (k == 1) { idx = 2; flags = 2; }
+                    else if (k == 2) { idx = 2; flags = 4; }
+                } else if (P.env_id == CADM_ENV_ANT) {
+                    idx = k + 1;                                  // o[1:]
+                }
+                base = (int)L.off_s + idx * 4; stride = (D + 1) * 4;
+                mean = P.obs_mean[k]; inv = 1.0f / (P.obs_std[k] + 1e-10f);
+            } else if (k < P.P + A) {
+                const int ai = k - P.P;
+                base = (int)L.off_act + ai * 4; stride = A * 4; flags = 1;
+                if (P.discrete) { mean = 0.f; inv = 1.f; }
+                else { mean = P.act_mean[ai]; inv = 1.0f / (P.act_std[ai] + 1e-10f); }
+            } else if (k < P.In) {
+                base = (int)L.off_ctx + (k - P.P - A) * 4; stride = P.C * 4; mean = 0.f; inv = 1.f;
+            }
+            feat_i[k] = make_int4(base, stride, flags, 0);
+            feat_f[k] = make_float2(mean, inv * tc::kXScale);
+        }
+        if (et == 0) *reinterpret_cast<float*>(smem + L.off_zero) = 0.f;
+
+        for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
+            const int e = tile / T.tiles_per_member;
+            const int tile_row0 = (tile - e * T.tiles_per_member) * P.rows_per_cta;
+            const int nrows = min(P.rows_per_cta, P.rows_per_member - tile_row0);
+            ptx::bar_sync(1, kSEpiThreads);             // previous tile fully retired before its smem is reused
+            for (int i = et; i < P.n_hidden * T.Np + T.NHp; i += kSEpiThreads)      // hidden-layer biases pre-scaled by kXScale
+                bias[i] = P.bpack[(size_t)e * P.bias_stride + i] * (i < P.n_hidden * T.Np ? tc::kXScale : 1.0f);
+            if (et < N) {
+                const int r = et;
+                int mi = 0, src = 0, pi = 0, cidx = 0, rid = 0, er = 0;
+                if (r < nrows) {
+                    const int rl = tile_row0 + r;
+                    if (P.row_mode == kRowsPlanner) {
+                        int nl;
+                        planner_row(P, e, rl, mi, nl, pi);
+                        src = mi * P.n_local + nl;
+                        const int ng = P.n_offset + nl;
+                        rid = (mi * P.n_global + ng) * P.p + pi;
+                        cidx = P.ctx_mode ? planner_ctx_index(P, e, mi, pi) : 0;
+                        const int jq = pi - e * P.q;
+                        er = e * (P.q * P.m * P.n_global) + (jq * P.m + mi) * P.n_global + ng;
+                    } else {
+                        src = e * P.rows_per_member + rl;
+                        rid = src; cidx = src; er = src;
+                    }
+                }
+                r_mi[r] = mi; r_src[r] = src; r_pi[r] = pi; r_ctx[r] = cidx; r_rid[r] = rid; r_eps[r] = er;
+            }
+            ptx::bar_sync(1, kSEpiThreads);
+            for (int i = et; i < N * D; i += kSEpiThreads) {
+                const int r = i / D, d = i - r * D;
+                float v = 0.f;
+                if (r < nrows) v = (P.row_mode == kRowsPlanner) ? P.obs0[r_mi[r] * D + d] : P.obs0[(size_t)r_src[r] * D + d];
+                S[r * (D + 1) + d] = v;
+            }
+            for (int i = et; i < N * P.C; i += kSEpiThreads) {
+                const int r = i / P.C, c = i - r * P.C;
+                ctx_s[i] = r < nrows ? __ldg(P.ctx + (size_t)r_ctx[r] * P.C + c) : 0.f;
+            }
+            auto prefetch_actions = [&](int t) {
+                if (P.discrete && P.row_mode == kRowsPlanner) return;
+                float* dst = act_s + (t & 1) * N * A;
+                for (int i = et; i < nrows * A; i += kSEpiThreads) {
+                    const int r = i / A, a = i - r * A;
+                    tcs::cp_async4(dst + i, P.actions + ((size_t)r_src[r] * P.h + t) * A + a);
+                }
+                tcs::cp_async_commit();
+            };
+            for (int i = et; i < 2 * N * A; i += kSEpiThreads) act_s[i] = 0.f;   // rows >= nrows stay finite
+            ptx::bar_sync(1, kSEpiThreads);
+            prefetch_actions(0);
+            tcs::cp_async_wait_all();
+            ptx::bar_sync(1, kSEpiThreads);
+
+            float ret = 0.f;                               // return of row `et` (threads et < nrows)
+#pragma unroll 1
+            for (int t = 0; t < P.h; ++t) {
+                long long* dbg = (T.dbg && blockIdx.x == 0 && ew == 2 && lane == 0 && tile == (int)blockIdx.x && t < 64) ? T.dbg + t * 64 : nullptr;
+                if (dbg) dbg[0] = clock64();
+                if (t + 1 < P.h) prefetch_actions(t + 1);                            // lands during this step
+                // ---------- prologue: reward of the current state; layer-0 input ------------------------
+                if (et < nrows) {
+                    const float* s = S + et * (D + 1);
+                    const float* arow = act_s + (t & 1) * N * A + et * A;
+                    if (env_reward_reads_next(P.env_id)) {
+                        if (t > 0) ret += env_reward_next(P.env_id, s);
+                    } else {
+                        ret += env_reward_current(P.env_id, s, arow, A, P.max_torque);
+                    }
+                }
+                {
+                    const int par_off = (t & 1) * N * A * 4;
+                    const bool onehot_mode = P.discrete && P.row_mode == kRowsPlanner;
+                    for (int i = et; i < K0 * (N >> 3); i += kSEpiThreads) {
+                        const int rg = i / K0, k = i - rg * K0;
+                        const int4 fi = feat_i[k];
+                        const float2 ff = feat_f[k];
+                        float y[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const int r = rg * 8 + jj;
+                            float src = *reinterpret_cast<const float*>(smem + fi.x + r * fi.y + ((fi.z & 1) ? par_off : 0));
+                            if (fi.z & 6) {
+                                float sn, cs;
+                                sincosf(src, &sn, &cs);
+                                src = (fi.z & 2) ? sn : cs;
+                            }
+                            if (onehot_mode && (fi.z & 1)) {
+                                const int oh = r < nrows ? __ldg(P.actions_int + (size_t)r_src[r] * P.h + t) : -1;
+                                src = (oh == k - P.P) ? 1.f : 0.f;
+                            }
+                            y[jj] = r < nrows ? (src - ff.x) * ff.y : 0.f;
+                        }
+                        tcs::store_rows8(xhi, xlo, xsbo, rg, k, y);
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&xr[mtg]);
+                }
+                if (dbg) dbg[1] = clock64();
+                // ---------- hidden layers: accumulator -> bias + swish -> next layer's B operand ----------
+#pragma unroll 1
+                for (int l = 0; l < P.n_hidden; ++l) {
+                    const uint32_t buf = g_count & 1u;
+                    const uint32_t par0 = (g_count >> 1) & 1u;
+                    const uint32_t par1 = c1cnt[buf] & 1u;
+                    ++g_count;
+                    if (T.nmt == 2) ++c1cnt[buf];
+                    const int my_mt = mtg < T.nmt ? mtg : T.nmt - 1;
+                    ptx::mbar_wait(&acc_full[buf * 2u + my_mt], my_mt ? par1 : par0);
+                    tc::fence_after_sync();
+                    if (dbg && l < 4) dbg[2 + 2 * l] = clock64();
+                    const bool warp_active = mtg < T.nmt && (mtg * 128 + quarter * 32) < T.Np;
+                    uint32_t hq[4][4], lq[4][4];
+                    if (warp_active) {
+                        const uint32_t tcol = tmem_lane + (buf * 2u + (uint32_t)mtg) * kSAccCols + (uint32_t)col0;
+                        const float b8 = jh < T.Np ? bias[l * T.Np + jh] : 0.f;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (c < nch) {
+                                uint32_t v[8];
+                                tc::tmem_ld8(tcol + c * 8, v);
+                                tc::tmem_wait_ld();
+                                float y[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) y[j] = tc::swish8_fast(fmaf(__uint_as_float(v[j]), 1.0f / tc::kWScale, b8));
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) tc::split2(y[2 * j], y[2 * j + 1], hq[c][j], lq[c][j]);
+                            }
+                        }
+                    }
+                    // M tile 1's MMAs still read the layer input: tile 0 stores only after they have completed
+                    if (mtg == 0 && T.nmt == 2) ptx::mbar_wait(&acc_full[buf * 2u + 1u], par1);
+                    if (warp_active && jh < T.Np) {
+                        const int rg0 = col0 >> 3;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (c < nch) {
+                                const int o = (rg0 + c) * xsbo + (jh >> 3) * 128 + (jh & 7) * 16;
+                                *reinterpret_cast<uint4*>(xhi + o) = make_uint4(hq[c][0], hq[c][1], hq[c][2], hq[c][3]);
+                                *reinterpret_cast<uint4*>(xlo + o) = make_uint4(lq[c][0], lq[c][1], lq[c][2], lq[c][3]);
+                            }
+                        }
+                    }
+                    tc::fence_before_sync();
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&xr[mtg]);
+                    if (dbg && l < 4) dbg[3 + 2 * l] = clock64();
+                }
+
+                // ---------- heads -> Hd[j][row] --------------------------------------------------------
+                {
+                    const uint32_t buf = g_count & 1u;
+                    const uint32_t par0 = (g_count >> 1) & 1u;
+                    ++g_count;
+                    if (mtg == 0 && quarter * 32 < T.NHp) {
+                        ptx::mbar_wait(&acc_full[buf * 2u], par0);
+                        tc::fence_after_sync();
+                        if (dbg) dbg[10] = clock64();
+                        const uint32_t tcol = tmem_lane + (buf * 2u) * kSAccCols + (uint32_t)col0;
+                        const float bj = jh < T.NHp ? bias[P.n_hidden * T.Np + jh] : 0.f;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (c < nch) {
+                                uint32_t v[8];
+                                tc::tmem_ld8(tcol + c * 8, v);
+                                tc::tmem_wait_ld();
+                                if (jh < T.NHp) {
+                                    float4 a, b;
+                                    const float sc = 1.0f / (tc::kWScale * tc::kXScale);
+                                    a.x = fmaf(__uint_as_float(v[0]), sc, bj); a.y = fmaf(__uint_as_float(v[1]), sc, bj);
+                                    a.z = fmaf(__uint_as_float(v[2]), sc, bj); a.w = fmaf(__uint_as_float(v[3]), sc, bj);
+                                    b.x = fmaf(__uint_as_float(v[4]), sc, bj); b.y = fmaf(__uint_as_float(v[5]), sc, bj);
+                                    b.z = fmaf(__uint_as_float(v[6]), sc, bj); b.w = fmaf(__uint_as_float(v[7]), sc, bj);
+                                    float* dst = Hd + jh * N + col0 + c * 8;
+                                    *reinterpret_cast<float4*>(dst) = a;
+                                    *reinterpret_cast<float4*>(dst + 4) = b;
+                                }
+                            }
+                        }
+                        tc::fence_before_sync();
+                    }
+                }
+                ptx::bar_sync(1, kSEpiThreads);
+                if (dbg) dbg[11] = clock64();
+
+                // ---------- final epilogue: sample, next state; work item = (row, block of 4 state dims) ----
+                for (int i = et; i < N * nj; i += kSEpiThreads) {
+                    const int jb = i / N, r = i - jb * N;
+                    if (r >= nrows) continue;
+                    const int d0 = 4 * jb;
+                    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (!P.deterministic) {
+                        if (P.eps != nullptr) {
+                            const float* ep = P.eps + (P.row_mode == kRowsPlanner ? (size_t)t * eps_step_stride : 0) + (size_t)r_eps[r] * D;
+#pragma unroll
+                            for (int ii = 0; ii < 4; ++ii) nz[ii] = d0 + ii < D ? __ldg(ep + d0 + ii) : 0.f;
+                        } else {
+                            normal4_fast(P.seed, (uint32_t)jb, (uint32_t)r_rid[r], (uint32_t)t, (uint32_t)P.it, nz);
+                        }
+                    }
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const int d = d0 + ii;
+                        if (d >= D) break;
+                        const float mu = Hd[d * N + r];
+                        float lv = Hd[(D + d) * N + r];
+                        const float dmu = mu * v_dscale[d] + v_dmean[d];
+                        float delta = dmu;
+                        if (!P.deterministic) {
+                            lv = fast_bounded_logvar(lv, v_maxlv[d], v_minlv[d]);
+                            delta = dmu + nz[ii] * fast_exp((lv + v_2logstd[d]) * 0.5f);
+                        }
+                        float* sp = S + r * (D + 1) + d;
+                        const float sn = env_postproc(P.env_id, *sp, delta, d);
+                        *sp = sn;
+                        if (P.row_mode == kRowsPlanner) {
+                            if (P.states != nullptr)
+                                P.states[(((size_t)t * P.m * P.n_local + r_src[r]) * P.p + r_pi[r]) * D + d] = sn;
+                        } else {
+                            const size_t o = (size_t)r_src[r] * D + d;
+                            if (P.next_obs) P.next_obs[o] = sn;
+                            if (P.mu_out) P.mu_out[o] = mu;
+                            if (P.lv_out) P.lv_out[o] = lv;
+                        }
+                    }
+                }
+                tcs::cp_async_wait_all();                  // next step's actions have landed (issued at the top of the step)
+                ptx::bar_sync(1, kSEpiThreads);
+                if (dbg) dbg[12] = clock64();
+            }
+            if (P.row_mode == kRowsPlanner && et < nrows) {
+                if (env_reward_reads_next(P.env_id)) ret += env_reward_next(P.env_id, S + et * (D + 1));
+                P.ret_p[(size_t)r_src[et] * P.p + r_pi[et]] = ret;
+            }
+        }
+    }
+
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, 4 * kSAccCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int g_tcs_smem = 0;
+
+// rows per tile: the smallest estimated launch time over N = 16, 32, 48, 64.  A step costs about 2500 cycles of serial
+// prologue / final epilogue plus 145 cycles of tensor work per row (3 terms), or the weight stream: `stream_bytes` per
+// step per CTA at min(64 B/clk per SM, 6000 B/clk / active CTAs).
+int tcs_pick_rows(int rows_per_member, int E, int num_sms, long long stream_bytes) {
+    int best = 16;
+    double best_cost = 1e30;
+    for (int N = 16; N <= kSMaxRows; N += 16) {
+        const int tiles = E * ((rows_per_member + N - 1) / N);
+        const int waves = (tiles + num_sms - 1) / num_sms;
+        const int active = tiles < num_sms ? tiles : num_sms;
+        const double bw = 6000.0 / active < 64.0 ? 6000.0 / active : 64.0;
+        const double compute = 2500.0 + 145.0 * N;
+        const double stream = (double)stream_bytes / bw;
+        const double cost = waves * (compute > stream ? compute : stream);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = N; }
+    }
+    return best;
+}
+
+cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long long wimg_member_stride, int terms, int kps,
+                               int rows_override, int num_sms, cudaStream_t stream, const char** name, long long* dbg) {
+    TcsParams T{};
+    T.dbg = dbg;
+    T.wimg = wimg;
+    T.wimg_member_stride = wimg_member_stride;
+    T.Np = round_up(P.H, 16);
+    T.NHp = round_up(2 * P.D, 16);
+    T.nkb0 = round_up(P.In, 16) / 16;
+    T.nkbH = T.Np / 16;
+    T.Kcap = max(T.Np, T.nkb0 * 16);
+    T.terms = terms;
+    T.kps = kps;
+    T.nmt = T.Np > 128 ? 2 : 1;
+    if (T.Np > 256 || T.NHp > 128 || kps < 1 || kps > kSMaxKps) return cudaErrorInvalidConfiguration;
+    int N = rows_override > 0 ? rows_override : tcs_pick_rows(P.rows_per_member, P.E, num_sms, wimg_member_stride);
+    N = min(kSMaxRows, max(16, round_up(N, 16)));
+    int tiles = (P.rows_per_member + N - 1) / N;
+    N = min(N, round_up((P.rows_per_member + tiles - 1) / tiles, 16));      // balance the rows over the tiles
+    P.rows_per_cta = min(N, (P.rows_per_member + tiles - 1) / tiles);
+    tiles = (P.rows_per_member + P.rows_per_cta - 1) / P.rows_per_cta;
+    T.N = N;
+    T.tiles_per_member = tiles;
+    T.total_tiles = tiles * P.E;
+    int stages = kSMaxStages;
+    while (stages > 2 && tcs_smem_layout(N, P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, T.Kcap, kps, stages).total > 226 * 1024) --stages;
+    T.stages = stages;
+    const TcsSmem L = tcs_smem_layout(N, P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, T.Kcap, kps, stages);
+    if (L.total > 226 * 1024) return cudaErrorInvalidConfiguration;
+    T.R = P;
+    if ((int)L.total > g_tcs_smem) {
+        cudaError_t e = cudaFuncSetAttribute(rollout_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        if (e != cudaSuccess) return e;
+        g_tcs_smem = (int)L.total;
+    }
+    if (name) *name = terms == 3 ? "rollout_tcs_kernel(swapped operands, fp16 hi/lo x3)" : "rollout_tcs_kernel(swapped operands, f16 x1)";
+    const int grid = min(T.total_tiles, num_sms);
+    rollout_tcs_kernel<<<grid, kSThreads, L.total, stream>>>(T);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-test: out[rows, Nout] = X[rows, K] * W[K, Nout] with exactly the operand layouts, descriptors, staging and split
+// arithmetic of rollout_tcs_kernel (device diagnostic behind cadm_selftest_tcs_gemm; tests compare with fp64).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) tcs_gemm_selftest_kernel(const float* __restrict__ X, const unsigned char* wimg, int rows,
+                                                                    int K, int Nout, int kps, int terms, float* __restrict__ out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int nkb = (K + 15) / 16;
+    const int Npad = round_up(Nout, 16);
+    const int Kcap = nkb * 16;
+    const int xsbo = (Kcap / 8) * 128;
+    const int xbytes = (rows / 8) * xsbo;
+    unsigned char* xhi = smem;
+    unsigned char* xlo = smem + xbytes;
+    unsigned char* wst = smem + (2 * xbytes + 127) / 128 * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wst + kps * 8192);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        ptx::mbar_init(&bars[0], 1);
+        ptx::mbar_init(&bars[1], 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_alloc(tmem_slot, 128);
+        tc::tmem_relinquish();
+    }
+    for (int i = tid; i < Kcap * (rows / 8); i += 128) {
+        const int rg = i / Kcap, k = i - rg * Kcap;
+        float y[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) y[jj] = k < K ? X[(size_t)(rg * 8 + jj) * K + k] * tc::kXScale : 0.f;
+        tcs::store_rows8(xhi, xlo, xsbo, rg, k, y);
+    }
+    ptx::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nmt = (Npad + 127) >> 7;
+    if (tid == 0) {
+        const uint32_t xhi_a = ptx::smem_u32(xhi), xlo_a = ptx::smem_u32(xlo), w_a = ptx::smem_u32(wst);
+        uint32_t ph = 0;
+        size_t off = 0;
+        for (int mt = 0; mt < nmt; ++mt) {
+            const int R = min(128, Npad - 128 * mt);
+            for (int s0 = 0; s0 < nkb; s0 += kps) {
+                const int kbs = min(kps, nkb - s0);
+                const uint32_t bytes = (uint32_t)kbs * 64u * (uint32_t)R;
+                ptx::mbar_arrive_expect_tx(&bars[0], bytes);
+                ptx::bulk_g2s(wst, wimg + off, bytes, &bars[0]);
+                off += bytes;
+                ptx::mbar_wait(&bars[0], ph);
+                tc::fence_after_sync();
+                tcs::issue_stage(tmem_base + mt * kSAccCols, w_a, R, kbs, s0, xhi_a, xlo_a, (uint32_t)xsbo, tcs::idesc((uint32_t)rows), terms);
+                tc::mma_commit(&bars[1]);
+                ptx::mbar_wait(&bars[1], ph);          // serialise: the single weight slot is reused
+                ph ^= 1u;
+            }
+        }
+    }
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int mt = 0; mt < nmt; ++mt) {
+        const int j = mt * 128 + tid;
+        for (int c = 0; c < rows; c += 8) {
+            uint32_t v[8];
+            tc::tmem_ld8(tl + mt * kSAccCols + c, v);
+            tc::tmem_wait_ld();
+            if (j < Nout) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) out[(size_t)(c + q) * Nout + j] = __uint_as_float(v[q]) * (1.0f / (tc::kWScale * tc::kXScale));
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, 128);
+    }
+}
+
+cudaError_t launch_tcs_gemm_selftest(const float* X, const unsigned char* wimg, int rows, int K, int Nout, int kps, int terms,
+                                     float* out, cudaStream_t stream) {
+    const int nkb = (K + 15) / 16;
+    const int xbytes = (rows / 8) * (nkb * 16 / 8) * 128;
+    const int smem_bytes = (2 * xbytes + 127) / 128 * 128 + kps * 8192 + 64;
+    cudaError_t e = cudaFuncSetAttribute(tcs_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    tcs_gemm_selftest_kernel<<<1, 128, smem_bytes, stream>>>(X, wimg, rows, K, Nout, kps, terms, out);
+    return cudaGetLastError();
+}
+
+}  // namespace cadm

@@ -4,6 +4,7 @@ PyTorch is used for device memory and streams only; every computation happens in
 All tensors handed to the engine are float32 CUDA tensors (int32 for discrete action ids).
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -91,6 +92,10 @@ class PlannerEngine:
         with torch.cuda.device(self.device):
             ccfg = cfg.to_c()
             check(None, self.lib.cadm_plan_create(C.byref(ccfg), C.byref(self._h)))
+        # tuning knobs of the tensor-core path (diagnostics / sweeps; the defaults are what bench.py measures)
+        for opt, env in (("tc_variant", "CADM_TC_VARIANT"), ("tcs_rows", "CADM_TCS_ROWS"), ("tcs_kps", "CADM_TCS_KPS")):
+            if os.environ.get(env):
+                self.set_option(opt, int(os.environ[env]))
         self.In = cfg.proc_obs_dim + cfg.act_dim + cfg.ctx_dim
         self.n_local = cfg.candidates // cfg.world
         self._keep = []      # tensors the engine borrowed asynchronously
@@ -287,6 +292,10 @@ class PlannerEngine:
         self._chk(self.lib.cadm_set_precision(self._h, _lib.PRECISIONS[precision]))
         self.cfg.precision = precision
 
+    def set_option(self, name: str, value: int):
+        """cadm_set_option: "tc_variant" (0 auto / 1 row tiles / 2 swapped operands), "tcs_rows", "tcs_kps"."""
+        self._chk(self.lib.cadm_set_option(self._h, name.encode(), int(value)))
+
     # ------------------------------------------------------------------ instrumentation
     @property
     def launch_count(self) -> int:
@@ -319,4 +328,17 @@ def selftest_tc_gemm(X: torch.Tensor, W: torch.Tensor, terms: int = 3) -> torch.
     with torch.cuda.device(X.device):
         check(None, lib.cadm_selftest_tc_gemm(_ptr(X), _ptr(W), X.shape[1], W.shape[1], terms, _ptr(out),
                                               C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)))
+    return out
+
+
+def selftest_tcs_gemm(X: torch.Tensor, W: torch.Tensor, kps: int = 2, terms: int = 3) -> torch.Tensor:
+    """out[rows, N] = X[rows, K] @ W[K, N] on the swapped-operand tensor-core path (rollout_tcs.cu; device diagnostic)."""
+    lib = _lib.load()
+    X = X.to(dtype=torch.float32).contiguous()
+    W = W.to(dtype=torch.float32).contiguous()
+    assert X.is_cuda and W.is_cuda and X.shape[1] == W.shape[0]
+    out = torch.empty((X.shape[0], W.shape[1]), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        check(None, lib.cadm_selftest_tcs_gemm(_ptr(X), _ptr(W), X.shape[0], X.shape[1], W.shape[1], kps, terms, _ptr(out),
+                                               C.c_void_p(torch.cuda.current_stream(X.device).cuda_stream)))
     return out

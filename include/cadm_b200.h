@@ -184,9 +184,25 @@ int cadm_set_precision(void* handle, int32_t precision);
  * K <= 208, N a multiple of 16 <= 208.  Synchronises.  Diagnostic only. */
 int cadm_selftest_tc_gemm(const float* X, const float* W, int32_t K, int32_t N, int32_t terms, float* out, void* stream);
 
-/* Diagnostic micro-benchmark: n_mma back-to-back tcgen05.mma (M=128, N, K=16, fp16) on resident shared-memory operands;
- * cycles_host[0] = issue time, cycles_host[1] = time until the commit is observed (clock64 cycles). */
-int cadm_selftest_tc_rate(int32_t N, int32_t n_mma, int32_t a_lbo, int64_t* cycles_host);
+/* Same for the swapped-operand kernel (rollout_tcs.cu): out[rows, N] = X[rows, K] * W[K, N] with the weights on the MMA's
+ * M axis (two M = 128 tiles when N > 128), the rows on its N axis (MN-major B operand) and `kps` K16 blocks per weight
+ * stage.  rows in {16, 32, 48, 64}, K <= 208, N <= 256.  Synchronises.  Diagnostic only. */
+int cadm_selftest_tcs_gemm(const float* X, const float* W, int32_t rows, int32_t K, int32_t N, int32_t kps, int32_t terms,
+                           float* out, void* stream);
+
+/* Tuning knobs of the tensor-core path (the defaults are what bench.py measures):
+ *   "tc_variant"  0 = pick by batch size, 1 = 128-row tiles (rollout_tc.cu), 2 = swapped operands (rollout_tcs.cu)
+ *   "tcs_rows"    rows per tile of the swapped kernel: 0 = pick, else 16 / 32 / 48 / 64
+ *   "tcs_kps"     K16 blocks per weight stage of the swapped kernel's image, 1..4 (before cadm_plan_set_weights) */
+int cadm_set_option(void* handle, const char* name, int32_t value);
+
+/* Diagnostic micro-benchmark: n_mma back-to-back tcgen05.mma (M=128, N, K=16, fp16) on resident shared-memory operands,
+ * round-robin over n_acc accumulators (1, 2, 4 or 8; 1 = each MMA depends on the previous one), in the operand layouts of
+ * rollout_tc.cu (swapped = 0) or rollout_tcs.cu (swapped = 1).  a_lbo bits 16+ select the issue-loop style (0: elect per
+ * MMA, 1: one elected thread); background bit 0 = a concurrent bulk-copy stream into shared memory, bit 1 = a commit every
+ * 6 MMAs.  cycles_host[0] = issue time, [1] = time until the commit is observed (clock64), [2] = 8 KB copies completed. */
+int cadm_selftest_tc_rate(int32_t N, int32_t n_mma, int32_t a_lbo, int32_t n_acc, int32_t swapped, int32_t background,
+                          int64_t* cycles_host);
 
 /* Diagnostic: clock64 trace of CTA 0 of the last tensor-core rollout launched with timing enabled, [step][32] slots
  * (see rollout_tc.cu); copies `count` int64 values to the host.  Synchronises. */

@@ -22,9 +22,20 @@ def _model(config, m_max=4, **kw):
     return build_model(config, m_max=m_max, **kw)
 
 
-@pytest.fixture(scope="module", params=["fp32", "tc3x"])
+@pytest.fixture(scope="module", params=["fp32", "tc3x-tiles", "tc3x-swapped"])
 def precision(request):
-    return request.param
+    """fp32 FFMA path and both tensor-core kernels: 128-row tiles (rollout_tc.cu) and swapped operands (rollout_tcs.cu);
+    the variant is forced through the engine's CADM_TC_VARIANT knob (cadm_set_option "tc_variant")."""
+    import os
+    name, _, variant = request.param.partition("-")
+    old = os.environ.get("CADM_TC_VARIANT")
+    if variant:
+        os.environ["CADM_TC_VARIANT"] = {"tiles": "1", "swapped": "2"}[variant]
+    yield name
+    if old is None:
+        os.environ.pop("CADM_TC_VARIANT", None)
+    else:
+        os.environ["CADM_TC_VARIANT"] = old
 
 
 # ---------------------------------------------------------------------------------------------------
