@@ -55,6 +55,7 @@ SIGNATURES = {
     "cadm_selftest_tcs_gemm": (C.c_int, [_F, _F, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F, _P]),
     "cadm_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "cadm_selftest_tc_rate": (C.c_int, [C.c_int32] * 6 + [C.c_void_p]),
+    "cadm_selftest_tcs_rate": (C.c_int, [C.c_int32] * 5 + [C.c_void_p]),
     "cadm_debug_trace": (C.c_int, [_P, C.c_void_p, C.c_int32]),
     "cadm_launch_count": (C.c_int64, [_P]),
     "cadm_kernel_name": (C.c_char_p, [_P]),

@@ -31,7 +31,9 @@ struct Engine {
     unsigned char* wimg_s = nullptr;   // same weights packed for the swapped-operand kernel (rollout_tcs.cu)
     int tc_variant = 0;                // 0 auto, 1 row tiles (rollout_tc.cu), 2 swapped operands (rollout_tcs.cu)
     int tcs_rows = 0;                  // rows per tile of the swapped kernel (0 = pick)
-    int tcs_kps = 2;                   // K16 blocks per weight stage the swapped image is packed with
+    bool trace = false;                // clock64 phase trace of CTA 0 (perturbs that CTA: off unless asked for)
+    int tcs_skew = 0;                  // start-delay step (cycles) that de-phases the CTAs of the swapped kernel
+    int tcs_kps = 4;                   // K16 blocks per weight stage the swapped image is packed with
     float* bpack_tc = nullptr;
     int Np16 = 0, NHp16 = 0, nkb0 = 0, nkbH = 0;
     long long wimg_member_stride = 0, bias_stride_tc = 0;
@@ -155,11 +157,11 @@ int run_rollout(Engine* E, RolloutParams& P, cudaStream_t s) {
                 const bool swapped = E->tc_variant == 2 || (E->tc_variant == 0 && swapped_ok && 4 * tiles128 < 3 * E->num_sms);
                 const int terms = E->precision == CADM_PREC_TC_3X ? 3 : 1;
                 if (swapped)
-                    CU(E, launch_rollout_tcs(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_kps, E->tcs_rows, E->num_sms, s,
-                                             &E->kernel_name, E->timing ? E->dbg : nullptr));
+                    CU(E, launch_rollout_tcs(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_kps, E->tcs_rows, E->tcs_skew, E->num_sms, s,
+                                             &E->kernel_name, E->trace ? E->dbg : nullptr));
                 else
                     CU(E, launch_rollout_tc(P, E->wimg, E->wimg_member_stride, terms, E->num_sms, s, &E->kernel_name,
-                                            E->timing ? E->dbg : nullptr));
+                                            E->trace ? E->dbg : nullptr));
             }
             break;
         default:
@@ -707,6 +709,11 @@ int cadm_set_option(void* handle, const char* name, int32_t value) {
         if (value < 1 || value > 4) return fail(E, CADM_ERR_ARG, "tcs_kps must be in 1..4");
         if (E->have_weights) return fail(E, CADM_ERR_STATE, "tcs_kps must be set before cadm_plan_set_weights");
         E->tcs_kps = value;
+    } else if (k == "trace") {
+        E->trace = value != 0;
+    } else if (k == "tcs_skew") {
+        if (value < 0) return fail(E, CADM_ERR_ARG, "tcs_skew must be non-negative (bits 20+ are diagnostic switches)");
+        E->tcs_skew = value;
     } else {
         return fail(E, CADM_ERR_ARG, "unknown option: " + k);
     }
@@ -745,6 +752,24 @@ int cadm_selftest_tc_rate(int32_t N, int32_t n_mma, int32_t a_lbo, int32_t n_acc
     if (e == cudaSuccess) e = cudaMemset(src, 0x3c, 1 << 20);
     if (e == cudaSuccess) e = cudaMemset(d, 0, 4 * sizeof(long long));
     if (e == cudaSuccess) e = launch_tc_mma_rate(N, n_mma, a_lbo, n_acc, swapped, background, src, d, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 3 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaFree(src);
+    if (e != cudaSuccess) return fail(nullptr, CADM_ERR_CUDA, cudaGetErrorString(e));
+    return CADM_OK;
+}
+
+int cadm_selftest_tcs_rate(int32_t rows, int32_t iters, int32_t R, int32_t kps, int32_t mode, int64_t* cycles_host) {
+    if (rows < 16 || rows > 64 || rows % 16 || iters < 1 || R < 16 || R > 128 || R % 16 || kps < 1 || kps > 4 || !cycles_host)
+        return fail(nullptr, CADM_ERR_ARG, "bad arguments");
+    long long* d = nullptr;
+    unsigned char* src = nullptr;
+    cudaError_t e = cudaMalloc(&d, 4 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMalloc(&src, (1 << 20) + 32768);
+    if (e == cudaSuccess) e = cudaMemset(src, 0x3c, (1 << 20) + 32768);
+    if (e == cudaSuccess) e = cudaMemset(d, 0, 4 * sizeof(long long));
+    if (e == cudaSuccess) e = launch_tcs_mma_rate(rows, iters, R, kps, mode, src, d, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 3 * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(d);

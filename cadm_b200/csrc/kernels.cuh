@@ -67,11 +67,13 @@ cudaError_t launch_rollout_tc(RolloutParams P, const unsigned char* wimg, long l
 cudaError_t launch_pack_tc(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad,
                            long long member_stride, long long layer_off, int clear, cudaStream_t stream);
 cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long long wimg_member_stride, int terms, int kps,
-                               int rows_override, int num_sms, cudaStream_t stream, const char** name, long long* dbg);
+                               int rows_override, int skew, int num_sms, cudaStream_t stream, const char** name, long long* dbg);
 cudaError_t launch_pack_tcs(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad, int kps,
                             long long member_stride, long long layer_off, int clear, cudaStream_t stream);
 cudaError_t launch_tcs_gemm_selftest(const float* X, const unsigned char* wimg, int rows, int K, int Nout, int kps, int terms,
                                      float* out, cudaStream_t stream);
+cudaError_t launch_tcs_mma_rate(int rows, int iters, int R, int kps, int mode, const unsigned char* src, long long* cycles,
+                                cudaStream_t stream);
 cudaError_t launch_tc_mma_rate(int N, int n_mma, int a_lbo, int n_acc, int swapped, int bg, const unsigned char* bg_src,
                                long long* cycles, cudaStream_t stream);
 cudaError_t launch_tc_gemm_selftest(const float* X, const unsigned char* wimg, int K, int N, int terms, float* out,

@@ -10,17 +10,28 @@
 //                above 128 use two M = 128 tiles (the second one reads past its 80 rows into finite weight bytes; those
 //                accumulator lanes are never read back)
 //   B operand  = activations, MN-major (row index contiguous) no-swizzle core matrices: an epilogue thread owns ONE
-//                hidden unit (TMEM lane) and writes 8 consecutive rows as one 16-byte store
-//   precision  = fp16 hi/lo split x3 into one fp32 accumulator, exactly as rollout_tc.cu (same scales, same terms)
+//                hidden unit (TMEM lane) and writes 8 consecutive rows as one 16-byte store.  X_lo is laid out directly
+//                behind X_hi at the same 8-row-group stride, so ONE MMA with N = 2 x rows multiplies a weight block by
+//                [X_hi ; X_lo] (the weight block -- 4 KB, the dominant shared-memory fetch of a small-N MMA -- is read once)
+//   precision  = fp16 hi/lo split, the same three products as rollout_tc.cu, kept in three accumulator column ranges
+//                [W_hi X_hi | W_hi X_lo | W_lo X_hi] that the epilogue adds in fp32 (2 MMAs per K16 block instead of 3)
+//
+// Measured on B200 (tools/tc_rate.py): a kind::f16 MMA with M = 128 costs max(N / 2, 32 + N / 4) cycles -- below N = 128
+// the 4 KB A fetch from shared memory (128 B/clk) sets the pace, not the tensor pipe; and it needs a lean issue loop (one
+// elected thread inside a single elect.sync region: 40 cycles per N = 32 MMA, against ~100 when each MMA is elected
+// separately and ~300 with per-MMA index arithmetic).
 //
 // Warp roles (576 threads): warp 0 streams the member's weight image from L2 through a shared-memory ring (1-D bulk
-// async copies, one stage = up to `kps` K16 blocks of one M tile, hi + lo); warp 1 issues the MMAs (elect.sync);
-// warps 2-9 are the epilogue of M tile 0, warps 10-17 of M tile 1 (quarter = TMEM lane quarter, two column slices
-// each).  The MMAs of M tile 1 run while tile 0's epilogue computes; tile 0 defers its shared-memory stores until tile
-// 1's MMAs (which still read the layer input) have completed, and the next layer's first K blocks start while tile 1's
-// epilogue runs: the tensor pipe stays busy inside one dependent layer chain.
+// async copies, one stage = up to `kps` K16 blocks of one M tile, hi + lo); warp 1 = one elected thread walking a
+// per-step stage table (built once in shared memory) and issuing the MMAs; warps 2-9 are the epilogue of M tile 0,
+// warps 10-17 of M tile 1 (quarter = TMEM lane quarter, two column slices each).  The layer input is double-buffered, so
+// tile 0's epilogue stores while tile 1's MMAs still read the previous buffer, and the next layer's first 8 K blocks
+// (produced by tile 0) are issued straight behind tile 1's MMAs while tile 1's epilogue runs: the tensor pipe does not
+// drain between the layers of one dependent chain.
 // Everything else (prologue gather / normalise / reward, bounded logvar, Gaussian sample, obs_postproc --
 // cadm/dynamics/core/utils.py:141-168) matches rollout_tc.cu, re-indexed for rows-as-columns.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -31,12 +42,13 @@ namespace cadm {
 constexpr int kSEpiThreads = 512;
 constexpr int kSThreads = 64 + kSEpiThreads;
 constexpr int kSMaxRows = 64;                  // rows per tile (multiple of 16)
-constexpr int kSAccCols = 64;                  // TMEM columns reserved per accumulator (buffer, M tile)
+constexpr int kSAccStride = 256;               // TMEM columns between the accumulators of the two M tiles (3 x rows <= 256)
 constexpr int kSMaxStages = 16;
 constexpr int kSMaxKps = 4;
+constexpr int kSMaxEnt = 96;                   // stage-table entries per step
 
 struct TcsSmem {
-    size_t off_xhi, off_xlo, off_w, off_s, off_hd, off_bias, off_vec, off_rowi, off_feat, off_zero, off_act, off_ctx, off_bar, total;
+    size_t off_x, off_w, off_s, off_hd, off_bias, off_vec, off_rowi, off_feat, off_zero, off_act, off_ctx, off_tab, off_bar, total;
     int xbytes, slot_bytes;
 };
 
@@ -44,10 +56,9 @@ __host__ __device__ inline TcsSmem tcs_smem_layout(int N, int D, int A, int C, i
                                                    int stages) {
     TcsSmem L;
     size_t o = 0;
-    L.xbytes = (N / 8) * (Kcap / 8) * 128;
+    L.xbytes = (N / 8) * (Kcap / 8) * 128;       // one operand half (hi or lo) of one layer-input buffer
     L.slot_bytes = kps * 8192;
-    L.off_xhi = o; o += L.xbytes;
-    L.off_xlo = o; o += L.xbytes;
+    L.off_x = o; o += (size_t)4 * L.xbytes;      // two buffers x [hi | lo]
     o = (o + 127) / 128 * 128;
     L.off_w = o; o += (size_t)stages * L.slot_bytes;
     L.off_s = o; o += (size_t)round_up(N * (D + 1), 4) * 4;
@@ -61,7 +72,8 @@ __host__ __device__ inline TcsSmem tcs_smem_layout(int N, int D, int A, int C, i
     L.off_act = o; o += (size_t)2 * N * A * 4;
     L.off_ctx = o; o += (size_t)N * (C > 0 ? C : 1) * 4;
     o = (o + 15) / 16 * 16;
-    L.off_bar = o; o += (size_t)(2 * kSMaxStages + 2 + 4 + 2) * 8;   // w_full, w_empty, xr[2], acc_full[4], tmem slot
+    L.off_tab = o; o += (size_t)kSMaxEnt * 32;                        // stage table (copied from the kernel parameters)
+    L.off_bar = o; o += (size_t)(2 * kSMaxStages + 2 + 2 + 4) * 8;   // w_full, w_empty, xr[2], acc_full[2], tmem slot
     L.total = o;
     return L;
 }
@@ -139,26 +151,101 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// the MMAs of one weight stage: kbs K16 blocks x `terms` products into d_tmem
-__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t slot_addr, int R, int kbs, int kb0, uint32_t xhi_a,
-                                            uint32_t xlo_a, uint32_t xsbo, uint32_t idesc_v, int terms) {
+// The MMAs of one weight stage (KBS K16 blocks of one M tile), fully unrolled, descriptors advanced by constant adds.
+// TERMS == 3: per block  D[0, 2 rows) (+)= W_hi [X_hi ; X_lo]  (one MMA with N = 2 rows)  and  D[2 rows, 3 rows) (+)= W_lo X_hi;
+// TERMS == 1: D[0, rows) (+)= W_hi X_hi.   a_hi / a_lo / b are complete 64-bit shared-memory descriptors of the first block.
+template <int TERMS, int KBS>
+__device__ __forceinline__ void issue_blocks(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b, uint32_t a_step, uint32_t rows,
+                                             uint32_t idesc1, uint32_t idesc2, uint32_t accum) {
+#pragma unroll
+    for (int j = 0; j < KBS; ++j) {
+        const uint32_t acc = j == 0 ? accum : 1u;
+        if (TERMS == 3) {
+            tc::mma_f16_ss(d_tmem, a_hi, b, idesc2, acc);                   // W_hi [X_hi ; X_lo]
+            tc::mma_f16_ss(d_tmem + 2u * rows, a_lo, b, idesc1, acc);       // W_lo X_hi
+        } else {
+            tc::mma_f16_ss(d_tmem, a_hi, b, idesc1, acc);
+        }
+        a_hi += a_step; a_lo += a_step;      // two k-chunks of R rows x 16 B, in 16-byte units
+        b += 16u;                            // 256 B per K block
+    }
+}
+
+//   slot16    (shared-memory address >> 4) of the stage: [hi: 2 kbs k-chunks x (R rows x 16 B)] [lo: same]
+//   xhi16     (address >> 4) of the stage's first K block in the X_hi buffer; X_lo starts `rows / 8` row groups behind X_hi
+template <int TERMS>
+__device__ __forceinline__ void issue_stage(uint32_t d_tmem, uint32_t slot16, uint32_t R, int kbs, uint32_t accum, uint32_t xhi16,
+                                            uint32_t rows, uint32_t xsbo) {
     const uint32_t hi32 = (1u << 14);                                   // descriptor version 1 (bit 46)
-    const uint32_t a_hi32 = hi32 | (128u >> 4);                         // A: SBO = 128 B between 8-row groups
-    const uint32_t b_hi32 = hi32 | (xsbo >> 4);                         // B: SBO = stride between 8-row (N) groups
-    const uint32_t a_lbo = ((uint32_t)(16 * R) >> 4) << 16;             // A: LBO = stride between the two k-chunks
-    const uint32_t b_lbo = (128u >> 4) << 16;                           // B: LBO = stride between the two k-groups
-    const uint32_t lo_off = (uint32_t)kbs * 32u * (uint32_t)R;
-    for (int j = 0; j < kbs; ++j) {
-        const int kb = kb0 + j;
-        const uint32_t wa = slot_addr + (uint32_t)(2 * j) * 16u * (uint32_t)R;
-        const uint64_t a_hi = ((uint64_t)a_hi32 << 32) | ((wa >> 4) | a_lbo);
-        const uint64_t a_lo = ((uint64_t)a_hi32 << 32) | (((wa + lo_off) >> 4) | a_lbo);
-        const uint64_t b_hi = ((uint64_t)b_hi32 << 32) | (((xhi_a + kb * 256u) >> 4) | b_lbo);
-        const uint64_t b_lo = ((uint64_t)b_hi32 << 32) | (((xlo_a + kb * 256u) >> 4) | b_lbo);
-        tc::mma_f16_ss(d_tmem, a_hi, b_hi, idesc_v, kb > 0 ? 1u : 0u);
-        if (terms == 3) {
-            tc::mma_f16_ss(d_tmem, a_hi, b_lo, idesc_v, 1u);            // W_hi X_lo
-            tc::mma_f16_ss(d_tmem, a_lo, b_hi, idesc_v, 1u);            // W_lo X_hi
+    const uint64_t a_top = (uint64_t)(hi32 | (128u >> 4)) << 32;        // A: SBO = 128 B between 8-row groups
+    const uint64_t b_top = (uint64_t)(hi32 | (xsbo >> 4)) << 32;        // B: SBO = stride between 8-row (N) groups
+    const uint32_t a_lbo = R << 16;                                     // A: LBO = 16 R bytes between the two k-chunks
+    const uint32_t b_lbo = (128u >> 4) << 16;                           // B: LBO = 128 B between the two k-groups
+    const uint64_t a_hi = a_top | (slot16 | a_lbo);
+    const uint64_t a_lo = a_top | ((slot16 + (uint32_t)kbs * 2u * R) | a_lbo);
+    const uint64_t b = b_top | (xhi16 | b_lbo);
+    const uint32_t idesc1 = idesc(rows), idesc2 = idesc(2u * rows);
+    switch (kbs) {
+        case 1: issue_blocks<TERMS, 1>(d_tmem, a_hi, a_lo, b, 2u * R, rows, idesc1, idesc2, accum); break;
+        case 2: issue_blocks<TERMS, 2>(d_tmem, a_hi, a_lo, b, 2u * R, rows, idesc1, idesc2, accum); break;
+        case 3: issue_blocks<TERMS, 3>(d_tmem, a_hi, a_lo, b, 2u * R, rows, idesc1, idesc2, accum); break;
+        default: issue_blocks<TERMS, 4>(d_tmem, a_hi, a_lo, b, 2u * R, rows, idesc1, idesc2, accum); break;
+    }
+}
+
+// Ring position of the MMA thread (slot index + phase parity), advanced with two instructions per stage.
+struct RingPos {
+    uint32_t slot, phase;
+};
+
+// All stages of ONE GEMM with every loop bound a compile-time constant (the hot configurations): NKB K16 blocks, output
+// width NPAD (one or two M tiles), KPS blocks per stage, KB_SPLIT = first K block produced by the M-tile-1 epilogue warps
+// of the previous layer (0: wait for both groups up front).  Fully unrolled: per stage one mbarrier wait, 2 KPS
+// back-to-back UTCHMMAs whose descriptors differ by immediates, one or two commits -- about 30 instructions, so the lone
+// issuing thread keeps ahead of the tensor pipe (the table-driven loop needs ~150 per stage and does not).
+template <int TERMS, int NKB, int NPAD, int KPS, int KB_SPLIT>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t w16, uint32_t slot16, int nstage, RingPos& rp, uint32_t xg16,
+                                           uint32_t rows, uint32_t xsbo, uint64_t* w_full, uint64_t* w_empty, uint64_t* xr,
+                                           uint64_t* acc_full, uint32_t ev) {
+    const uint32_t hi32 = (1u << 14);
+    const uint64_t a_top = (uint64_t)(hi32 | (128u >> 4)) << 32;
+    const uint64_t b_top = (uint64_t)(hi32 | (xsbo >> 4)) << 32;
+    const uint32_t b_lbo = (128u >> 4) << 16;
+    const uint32_t idesc1 = idesc(rows), idesc2 = idesc(2u * rows);
+    constexpr int NMT = (NPAD + 127) / 128;
+    bool waited1 = false;
+    ptx::mbar_wait(&xr[0], ev);
+    if (KB_SPLIT == 0) { ptx::mbar_wait(&xr[1], ev); waited1 = true; }
+    tc::fence_after_sync();
+#pragma unroll
+    for (int mt = 0; mt < NMT; ++mt) {
+        constexpr int R0 = NPAD < 128 ? NPAD : 128;
+        const uint32_t R = mt == 0 ? (uint32_t)R0 : (uint32_t)(NPAD - 128);
+        const uint32_t d_tmem = tmem_base + (uint32_t)mt * kSAccStride;
+#pragma unroll
+        for (int s0 = 0; s0 < NKB; s0 += KPS) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int kbs = (NKB - s0) < KPS ? (NKB - s0) : KPS;
+            const bool last = mt == NMT - 1 && s0 + kbs >= NKB;
+            if (!waited1 && (s0 + kbs > KB_SPLIT || last)) {
+                ptx::mbar_wait(&xr[1], ev);
+                tc::fence_after_sync();
+                waited1 = true;
+            }
+            ptx::mbar_wait(&w_full[rp.slot], rp.phase);
+            const uint32_t slot = w16 + rp.slot * slot16;
+            const uint64_t a_hi = a_top | (slot | (R << 16));
+            const uint64_t a_lo = a_top | ((slot + (uint32_t)kbs * 2u * R) | (R << 16));
+            const uint64_t b = b_top | ((xg16 + (uint32_t)s0 * 16u) | b_lbo);
+            const uint32_t accum = s0 > 0 ? 1u : 0u;
+            if (kbs == 4) issue_blocks<TERMS, 4>(d_tmem, a_hi, a_lo, b, 2u * R, rows, idesc1, idesc2, accum);
+            else if (kbs == 3) issue_blocks<TERMS, 3>(d_tmem, a_hi, a_lo, b, 2u * R, rows, idesc1, idesc2, accum);
+            else if (kbs == 2) issue_blocks<TERMS, 2>(d_tmem, a_hi, a_lo, b, 2u * R, rows, idesc1, idesc2, accum);
+            else issue_blocks<TERMS, 1>(d_tmem, a_hi, a_lo, b, 2u * R, rows, idesc1, idesc2, accum);
+            tc::mma_commit(&w_empty[rp.slot]);
+            if (s0 + kbs >= NKB) tc::mma_commit(&acc_full[mt]);
+            if (++rp.slot == (uint32_t)nstage) { rp.slot = 0; rp.phase ^= 1u; }
         }
     }
 }
@@ -174,16 +261,22 @@ struct TcsParams {
     int N;                       // rows per tile (multiple of 16, <= kSMaxRows)
     int nmt;                     // M tiles of a hidden GEMM: 1 (Np <= 128) or 2
     int tiles_per_member, total_tiles;
+    int debug;                   // diagnostic bits: 1 no weight copies, 2 no hidden-layer epilogue work (results are garbage)
+    int skew;                    // start delay step in cycles (CTA i waits (i % 8) * skew)
+    int nent;                    // stages per horizon step
+    uint4 tab[2 * kSMaxEnt];     // the stage table (kernel-parameter space: uniform loads straight into uniform registers)
     long long* dbg;              // nullable: clock64 trace of CTA 0, [step][64]
 };
 
+// NKB0 > 0 selects the compile-time schedule of the MMA thread for the reference architecture (4 hidden layers of width
+// 193..208, KPS = 4): NKB0 = K16 blocks of layer 0, NHP = padded width of the heads.  NKB0 == 0: table-driven schedule.
+template <int TERMS, int NKB0, int NHP>
 __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_constant__ TcsParams T) {
     const RolloutParams& P = T.R;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int N = T.N;
     const TcsSmem L = tcs_smem_layout(N, P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, T.Kcap, T.kps, T.stages);
-    unsigned char* xhi = smem + L.off_xhi;
-    unsigned char* xlo = smem + L.off_xlo;
+    unsigned char* xbuf = smem + L.off_x;          // buffer b: X_hi at b * 2 xbytes, X_lo directly behind it
     unsigned char* wring = smem + L.off_w;
     float* S = reinterpret_cast<float*>(smem + L.off_s);
     float* Hd = reinterpret_cast<float*>(smem + L.off_hd);             // [NHp][N] head outputs
@@ -194,11 +287,13 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
     float2* feat_f = reinterpret_cast<float2*>(smem + L.off_feat + 96 * 16);
     float* act_s = reinterpret_cast<float*>(smem + L.off_act);
     float* ctx_s = reinterpret_cast<float*>(smem + L.off_ctx);
+    uint4* tab = reinterpret_cast<uint4*>(smem + L.off_tab);
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* w_empty = w_full + kSMaxStages;
     uint64_t* xr = w_empty + kSMaxStages;          // [2]: layer input produced by the M-tile-0 / M-tile-1 warps
-    uint64_t* acc_full = xr + 2;                   // [buffer][M tile]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 4);
+    uint64_t* acc_full = xr + 2;                   // [M tile]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    volatile uint32_t* done = tmem_slot + 1;       // [2]: the producer / MMA thread has finished (its warp's other lanes sleep on it)
 
     float* v_dmean = vec + 2 * kMaxObs + 2 * kMaxAct;
     float* v_dscale = v_dmean + kMaxObs;
@@ -215,24 +310,32 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int nstage = T.stages;
-    const int gemms_per_step = P.n_hidden + 1;
     const int xsbo = (T.Kcap / 8) * 128;
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
         ptx::mbar_init(&xr[0], 8);
         ptx::mbar_init(&xr[1], 8);
-        for (int i = 0; i < 4; ++i) ptx::mbar_init(&acc_full[i], 1);
+        ptx::mbar_init(&acc_full[0], 1);
+        ptx::mbar_init(&acc_full[1], 1);
+        done[0] = 0u;
+        done[1] = 0u;
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
         __syncwarp();
-        tc::tmem_alloc(tmem_slot, 4 * kSAccCols);
+        tc::tmem_alloc(tmem_slot, 512);
         tc::tmem_relinquish();
     }
+    for (int i = tid; i < 2 * T.nent; i += kSThreads) tab[i] = T.tab[i];
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    const int nent = T.nent;
+    if (T.skew > 0) {                              // de-phase the CTAs' weight-stream bursts (see launch_rollout_tcs)
+        const long long until = clock64() + (long long)(blockIdx.x % 8) * T.skew;
+        while (clock64() < until) __nanosleep(200);
+    }
 
     // ======================= warp 0: weight producer =============================================
     if (warp == 0) {
@@ -243,97 +346,144 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 const unsigned char* wsrc = T.wimg + (size_t)e * T.wimg_member_stride;
                 for (int t = 0; t < P.h; ++t) {
                     size_t off = 0;
-                    for (int g = 0; g < gemms_per_step; ++g) {
-                        const int nkb = g == 0 ? T.nkb0 : T.nkbH;
-                        const int Npad = g == P.n_hidden ? T.NHp : T.Np;
-                        const int nmt = (Npad + 127) >> 7;
-                        for (int mt = 0; mt < nmt; ++mt) {
-                            const int R = min(128, Npad - 128 * mt);
-                            for (int s0 = 0; s0 < nkb; s0 += T.kps) {
-                                const uint32_t bytes = (uint32_t)min(T.kps, nkb - s0) * 64u * (uint32_t)R;
-                                ptx::mbar_wait(&w_empty[rp.stage], rp.phase ^ 1u);
-                                ptx::mbar_arrive_expect_tx(&w_full[rp.stage], bytes);
-                                ptx::bulk_g2s(wring + (size_t)rp.stage * L.slot_bytes, wsrc + off, bytes, &w_full[rp.stage]);
-                                off += bytes;
-                                rp.advance();
-                            }
+                    for (int i = 0; i < nent; ++i) {
+                        const uint32_t bytes = tab[2 * i].y;
+                        ptx::mbar_wait(&w_empty[rp.stage], rp.phase ^ 1u);
+                        if (T.debug & 1) {                          // diagnostic: no weight traffic at all
+                            ptx::mbar_arrive(&w_full[rp.stage]);
+                        } else {
+                            ptx::mbar_arrive_expect_tx(&w_full[rp.stage], bytes);
+                            ptx::bulk_g2s(wring + (size_t)rp.stage * L.slot_bytes, wsrc + off, bytes, &w_full[rp.stage]);
                         }
+                        off += bytes;
+                        rp.advance();
                     }
                 }
             }
+            done[0] = 1u;
+        } else {
+            // A lane parked at a warp barrier keeps competing for issue slots with the working lane of its own warp
+            // (measured: the single-thread loops run ~2x slower); sleeping lanes do not.
+            while (!done[0]) __nanosleep(2000);
         }
+        __syncwarp();
     }
     // ======================= warp 1: MMA issuer ==================================================
-    // ONE elected thread runs the whole MMA schedule (waits included): inside an elect.sync region ptxas keeps the
-    // descriptors in uniform registers and the UTCHMMAs issue back to back -- measured 40 cycles per MMA at N = 32..64
-    // (the shared-memory operand fetch: 4 KB of A per MMA), against ~100 when every MMA is elected separately.
+    // ONE elected thread walks the stage table: inside a single elect.sync region ptxas keeps the descriptors in uniform
+    // registers and the UTCHMMAs issue back to back.  A lone thread has no latency hiding, and its ~400 cycles of
+    // per-stage bookkeeping (table decode, descriptor arithmetic, mbarrier try_wait, ring advance) cost as much as the
+    // stage's MMAs take to execute -- so the NEXT stage is prepared in the middle of the current stage's MMA sequence,
+    // while the first half of its MMAs keeps the tensor pipe fed.
     else if (warp == 1) {
-        if (ptx::elect_one()) {
-            tcs::Ring rc{0, 0, nstage};
-            uint32_t g_count = 0;
-            const uint32_t xhi_d = ptx::smem_u32(xhi) >> 4, xlo_d = ptx::smem_u32(xlo) >> 4, w_a = ptx::smem_u32(wring);
-            const uint32_t idesc_v = tcs::idesc((uint32_t)N);
+        if (NKB0 > 0) {
+            if (ptx::elect_one()) {
+                const uint32_t x16 = ptx::smem_u32(xbuf) >> 4, w16 = ptx::smem_u32(wring) >> 4, slot16 = (uint32_t)L.slot_bytes >> 4;
+                const uint32_t xb1 = x16 + ((uint32_t)(2 * L.xbytes) >> 4);     // layer-input buffer 1
+                tcs::RingPos rp{0u, 0u};
+                uint32_t ev = 0;
+                for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
+                    for (int t = 0; t < P.h; ++t) {
+                        long long* dbg = (T.dbg && blockIdx.x == 0 && tile == (int)blockIdx.x && t < 64) ? T.dbg + t * 64 + 32 : nullptr;
+                        if (dbg) dbg[0] = clock64();
+                        tcs::issue_gemm<TERMS, NKB0, 208, 4, 0>(tmem_base, w16, slot16, nstage, rp, x16, (uint32_t)N, (uint32_t)xsbo, w_full,
+                                                                w_empty, xr, acc_full, ev);
+                        ev ^= 1u;
+                        if (dbg) { dbg[1] = clock64(); dbg[4] = dbg[1]; }
+                        tcs::issue_gemm<TERMS, 13, 208, 4, 8>(tmem_base, w16, slot16, nstage, rp, xb1, (uint32_t)N, (uint32_t)xsbo, w_full,
+                                                              w_empty, xr, acc_full, ev);
+                        ev ^= 1u;
+                        if (dbg) { dbg[5] = clock64(); dbg[8] = dbg[5]; }
+                        tcs::issue_gemm<TERMS, 13, 208, 4, 8>(tmem_base, w16, slot16, nstage, rp, x16, (uint32_t)N, (uint32_t)xsbo, w_full,
+                                                              w_empty, xr, acc_full, ev);
+                        ev ^= 1u;
+                        if (dbg) { dbg[9] = clock64(); dbg[12] = dbg[9]; }
+                        tcs::issue_gemm<TERMS, 13, 208, 4, 8>(tmem_base, w16, slot16, nstage, rp, xb1, (uint32_t)N, (uint32_t)xsbo, w_full,
+                                                              w_empty, xr, acc_full, ev);
+                        ev ^= 1u;
+                        if (dbg) { dbg[13] = clock64(); dbg[16] = dbg[13]; }
+                        tcs::issue_gemm<TERMS, 13, NHP, 4, 8>(tmem_base, w16, slot16, nstage, rp, x16, (uint32_t)N, (uint32_t)xsbo, w_full,
+                                                              w_empty, xr, acc_full, ev);
+                        ev ^= 1u;
+                        if (dbg) dbg[17] = clock64();
+                    }
+                }
+                done[1] = 1u;
+            } else {
+                while (!done[1]) __nanosleep(2000);
+            }
+        } else if (ptx::elect_one()) {
+            const uint32_t x16 = ptx::smem_u32(xbuf) >> 4, w16 = ptx::smem_u32(wring) >> 4, slot16 = (uint32_t)L.slot_bytes >> 4;
             const uint32_t hi32 = (1u << 14);                                   // descriptor version 1 (bit 46)
             const uint64_t a_top = (uint64_t)(hi32 | (128u >> 4)) << 32;        // A: SBO = 128 B between 8-row groups
             const uint64_t b_top = (uint64_t)(hi32 | ((uint32_t)xsbo >> 4)) << 32;   // B: SBO = stride between 8-row (N) groups
-            const uint32_t b_lbo = (128u >> 4) << 16;                           // B: LBO = stride between the two k-groups
-            for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
-                for (int t = 0; t < P.h; ++t) {
-                    for (int g = 0; g < gemms_per_step; ++g) {
-                        const int nkb = g == 0 ? T.nkb0 : T.nkbH;
-                        const int Npad = g == P.n_hidden ? T.NHp : T.Np;
-                        const int nmt = (Npad + 127) >> 7;
-                        const uint32_t buf = g_count & 1u;
-                        const uint32_t xpar = g_count & 1u;
-                        // K blocks [0, kb_split) come from the M-tile-0 warps of the producing phase, the rest from tile 1
-                        // (the prologue spreads layer 0 over all warps: wait for both up front)
-                        const int kb_split = (g == 0 || T.nmt == 1) ? 0 : 8;
-                        bool waited1 = false;
-                        long long* dbg = (T.dbg && blockIdx.x == 0 && tile == (int)blockIdx.x && t < 64 && g < 5)
-                                             ? T.dbg + t * 64 + 32 + 4 * g : nullptr;
-                        long long xw = 0, ww = 0;
-                        for (int mt = 0; mt < nmt; ++mt) {
-                            const uint32_t R = (uint32_t)min(128, Npad - 128 * mt);
-                            const uint32_t d_tmem = tmem_base + (buf * 2u + (uint32_t)mt) * kSAccCols;
-                            const uint32_t a_lbo = R << 16;                     // A: LBO = 16 R bytes between the two k-chunks
-                            for (int s0 = 0; s0 < nkb; s0 += T.kps) {
-                                const int kbs = min(T.kps, nkb - s0);
-                                const long long c0 = dbg ? clock64() : 0;
-                                if (mt == 0 && s0 == 0) ptx::mbar_wait(&xr[0], xpar);
-                                const bool last_stage = mt == nmt - 1 && s0 + kbs >= nkb;
-                                if (!waited1 && (s0 + kbs > kb_split || last_stage)) { ptx::mbar_wait(&xr[1], xpar); waited1 = true; }
-                                const long long c1 = dbg ? clock64() : 0;
-                                if (dbg && mt == 0 && s0 == 0) dbg[0] = c1;
-                                ptx::mbar_wait(&w_full[rc.stage], rc.phase);
-                                const long long c2 = dbg ? clock64() : 0;
-                                if (dbg) { xw += c1 - c0; ww += c2 - c1; }
-                                tc::fence_after_sync();
-                                const uint32_t slot = w_a + rc.stage * L.slot_bytes;
-                                uint32_t wa_hi = (slot >> 4) | a_lbo;                              // W_hi of the stage's first K block
-                                uint32_t wa_lo = ((slot + (uint32_t)kbs * 32u * R) >> 4) | a_lbo;  // W_lo
-                                uint32_t xb_hi = (xhi_d + (uint32_t)s0 * 16u) | b_lbo;             // X_hi (256 B per K block)
-                                uint32_t xb_lo = (xlo_d + (uint32_t)s0 * 16u) | b_lbo;
-                                uint32_t accum = s0 > 0 ? 1u : 0u;
-                                for (int j = 0; j < kbs; ++j) {
-                                    tc::mma_f16_ss(d_tmem, a_top | wa_hi, b_top | xb_hi, idesc_v, accum);
-                                    if (T.terms == 3) {
-                                        tc::mma_f16_ss(d_tmem, a_top | wa_hi, b_top | xb_lo, idesc_v, 1u);      // W_hi X_lo
-                                        tc::mma_f16_ss(d_tmem, a_top | wa_lo, b_top | xb_hi, idesc_v, 1u);      // W_lo X_hi
-                                    }
-                                    accum = 1u;
-                                    wa_hi += 2u * R; wa_lo += 2u * R;                // two k-chunks of R rows x 16 B, in 16-B units
-                                    xb_hi += 16u; xb_lo += 16u;
-                                }
-                                tc::mma_commit(&w_empty[rc.stage]);
-                                rc.advance();
-                            }
-                            tc::mma_commit(&acc_full[buf * 2u + (uint32_t)mt]);
-                        }
-                        if (dbg) { dbg[1] = clock64(); dbg[2] = xw; dbg[3] = ww; }
-                        ++g_count;
-                    }
-                }
+            const uint32_t b_lbo = (128u >> 4) << 16;                           // B: LBO = 128 B between the two k-groups
+            const uint32_t rows = (uint32_t)N;
+            const uint32_t idesc1 = tcs::idesc(rows), idesc2 = tcs::idesc(2u * rows);
+            int my_tiles = 0;
+            for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) ++my_tiles;
+            long long remaining = (long long)my_tiles * P.h * nent;
+            const bool trace = T.dbg != nullptr && blockIdx.x == 0;
+            // state of the stage being issued
+            uint32_t ev = 0;                       // parity of the layer-input event the next GEMM waits for
+            int stage = 0, ti = 0, tstep = 0;      // ring slot, table index, horizon step (trace only)
+            uint32_t phase = 0;
+            uint4 e0 = tab[0], e1 = tab[1];
+            // the first stage: blocking waits
+            if (remaining > 0) {
+                ptx::mbar_wait(&xr[0], ev);
+                ptx::mbar_wait(&xr[1], ev);
+                ptx::mbar_wait(&w_full[0], 0);
+                tc::fence_after_sync();
+                if (trace) T.dbg[32] = clock64();
             }
+            while (remaining > 0) {
+                --remaining;
+                const uint32_t R = e1.x, a_step = 2u * R;
+                const int kbs = (int)e1.y;
+                const uint32_t d_tmem = tmem_base + e0.w;
+                const uint32_t slot = w16 + (uint32_t)stage * slot16;
+                const uint64_t a_hi = a_top | (slot | (R << 16));
+                const uint64_t a_lo = a_top | ((slot + (uint32_t)kbs * a_step) | (R << 16));
+                const uint64_t b = b_top | ((x16 + e0.z) | b_lbo);
+                const bool skip = (T.debug & 4) != 0;
+                // ---- first half of the stage's MMAs
+                if (!skip) {
+                    tcs::issue_blocks<TERMS, 1>(d_tmem, a_hi, a_lo, b, a_step, rows, idesc1, idesc2, e1.z);
+                    if (kbs > 1) tcs::issue_blocks<TERMS, 1>(d_tmem, a_hi + a_step, a_lo + a_step, b + 16u, a_step, rows, idesc1, idesc2, 1u);
+                }
+                // ---- prepare the next stage under them
+                int nti = ti + 1, nstep = tstep;
+                if (nti == nent) { nti = 0; ++nstep; }
+                int nstg = stage + 1;
+                uint32_t nphase = phase;
+                if (nstg == nstage) { nstg = 0; nphase ^= 1u; }
+                const uint4 f0 = tab[2 * nti], f1 = tab[2 * nti + 1];
+                const uint32_t nev = (e0.x & 8u) ? (ev ^ 1u) : ev;
+                bool ready = false;
+                if (remaining > 0 && !(f0.x & 3u)) ready = ptx::mbar_try_wait(&w_full[nstg], nphase);
+                // ---- second half
+                if (!skip) {
+                    if (kbs > 2) tcs::issue_blocks<TERMS, 1>(d_tmem, a_hi + 2u * a_step, a_lo + 2u * a_step, b + 32u, a_step, rows, idesc1, idesc2, 1u);
+                    if (kbs > 3) tcs::issue_blocks<TERMS, 1>(d_tmem, a_hi + 3u * a_step, a_lo + 3u * a_step, b + 48u, a_step, rows, idesc1, idesc2, 1u);
+                }
+                tc::mma_commit(&w_empty[stage]);
+                if (e0.x & 4u) tc::mma_commit(&acc_full[(e0.x >> 4) & 1u]);
+                if (trace && (e0.x & 8u) && tstep < 64 && e1.w < 5) T.dbg[tstep * 64 + 32 + 4 * e1.w + 1] = clock64();
+                // ---- whatever the next stage still has to wait for
+                if (remaining > 0 && !ready) {
+                    if (f0.x & 1u) ptx::mbar_wait(&xr[0], nev);
+                    if (f0.x & 2u) ptx::mbar_wait(&xr[1], nev);
+                    ptx::mbar_wait(&w_full[nstg], nphase);
+                    // the accumulator / layer-input hand-over from the epilogue warps needs the tcgen05 fence; a weight
+                    // stage alone does not (async-proxy writes completed on the mbarrier)
+                    if (f0.x & 3u) tc::fence_after_sync();
+                    if (trace && (f0.x & 1u) && nstep < 64 && f1.w < 5) T.dbg[nstep * 64 + 32 + 4 * f1.w] = clock64();
+                }
+                e0 = f0; e1 = f1; ev = nev; stage = nstg; phase = nphase; ti = nti; tstep = nstep;
+            }
+            done[1] = 1u;
+        } else {
+            while (!done[1]) __nanosleep(2000);
         }
         __syncwarp();
     }
@@ -348,8 +498,9 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
         const int jh = mtg * 128 + quarter * 32 + lane;                 // hidden unit (TMEM lane of M tile mtg)
         const int nch = N >> 4;                        // 8-column chunks per column slice (N / 2 / 8)
         const int col0 = cslice * (N >> 1);
-        uint32_t g_count = 0;
-        uint32_t c1cnt[2] = {0u, 0u};                  // completions of acc_full[buf][1] so far
+        uint32_t g_count = 0;                          // GEMMs so far   = completions of acc_full[0]
+        uint32_t c1cnt = 0;                            // 2-tile GEMMs   = completions of acc_full[1]
+        unsigned char* const x0hi = xbuf;              // layer-input buffer 0 (layer 0 and every other layer after it)
         const int D = P.D, A = P.A;
         const size_t eps_step_stride = (size_t)P.E * P.q * P.m * P.n_global * D;
         const int nj = (D + 3) >> 2;                   // Philox blocks (4 state dims each) per row
@@ -484,7 +635,7 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                             }
                             y[jj] = r < nrows ? (src - ff.x) * ff.y : 0.f;
                         }
-                        tcs::store_rows8(xhi, xlo, xsbo, rg, k, y);
+                        tcs::store_rows8(x0hi, x0hi + L.xbytes, xsbo, rg, k, y);
                     }
                     ptx::fence_proxy_async();
                     __syncwarp();
@@ -494,44 +645,46 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 // ---------- hidden layers: accumulator -> bias + swish -> next layer's B operand ----------
 #pragma unroll 1
                 for (int l = 0; l < P.n_hidden; ++l) {
-                    const uint32_t buf = g_count & 1u;
-                    const uint32_t par0 = (g_count >> 1) & 1u;
-                    const uint32_t par1 = c1cnt[buf] & 1u;
-                    ++g_count;
-                    if (T.nmt == 2) ++c1cnt[buf];
                     const int my_mt = mtg < T.nmt ? mtg : T.nmt - 1;
-                    ptx::mbar_wait(&acc_full[buf * 2u + my_mt], my_mt ? par1 : par0);
+                    ptx::mbar_wait(&acc_full[my_mt], (my_mt ? c1cnt : g_count) & 1u);
+                    ++g_count;
+                    if (T.nmt == 2) ++c1cnt;
                     tc::fence_after_sync();
                     if (dbg && l < 4) dbg[2 + 2 * l] = clock64();
-                    const bool warp_active = mtg < T.nmt && (mtg * 128 + quarter * 32) < T.Np;
-                    uint32_t hq[4][4], lq[4][4];
-                    if (warp_active) {
-                        const uint32_t tcol = tmem_lane + (buf * 2u + (uint32_t)mtg) * kSAccCols + (uint32_t)col0;
+                    if (mtg < T.nmt && (mtg * 128 + quarter * 32) < T.Np && !(T.debug & 2)) {
+                        // GEMM l read buffer l & 1; its output (the input of GEMM l + 1) goes to the other buffer
+                        unsigned char* const xo_hi = xbuf + ((l + 1) & 1) * 2 * L.xbytes;
+                        unsigned char* const xo_lo = xo_hi + L.xbytes;
+                        const uint32_t tcol = tmem_lane + (uint32_t)mtg * kSAccStride + (uint32_t)col0;
                         const float b8 = jh < T.Np ? bias[l * T.Np + jh] : 0.f;
+                        const int rg0 = col0 >> 3;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             if (c < nch) {
                                 uint32_t v[8];
                                 tc::tmem_ld8(tcol + c * 8, v);
-                                tc::tmem_wait_ld();
+                                if (TERMS == 3) {
+                                    uint32_t v1[8], v2[8];
+                                    tc::tmem_ld8(tcol + N + c * 8, v1);
+                                    tc::tmem_ld8(tcol + 2 * N + c * 8, v2);
+                                    tc::tmem_wait_ld();
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        v[j] = __float_as_uint(__uint_as_float(v[j]) + (__uint_as_float(v1[j]) + __uint_as_float(v2[j])));
+                                } else {
+                                    tc::tmem_wait_ld();
+                                }
                                 float y[8];
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) y[j] = tc::swish8_fast(fmaf(__uint_as_float(v[j]), 1.0f / tc::kWScale, b8));
+                                if (jh < T.Np) {
+                                    uint32_t hq[4], lq[4];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) tc::split2(y[2 * j], y[2 * j + 1], hq[c][j], lq[c][j]);
-                            }
-                        }
-                    }
-                    // M tile 1's MMAs still read the layer input: tile 0 stores only after they have completed
-                    if (mtg == 0 && T.nmt == 2) ptx::mbar_wait(&acc_full[buf * 2u + 1u], par1);
-                    if (warp_active && jh < T.Np) {
-                        const int rg0 = col0 >> 3;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (c < nch) {
-                                const int o = (rg0 + c) * xsbo + (jh >> 3) * 128 + (jh & 7) * 16;
-                                *reinterpret_cast<uint4*>(xhi + o) = make_uint4(hq[c][0], hq[c][1], hq[c][2], hq[c][3]);
-                                *reinterpret_cast<uint4*>(xlo + o) = make_uint4(lq[c][0], lq[c][1], lq[c][2], lq[c][3]);
+                                    for (int j = 0; j < 4; ++j) tc::split2(y[2 * j], y[2 * j + 1], hq[j], lq[j]);
+                                    const int o = (rg0 + c) * xsbo + (jh >> 3) * 128 + (jh & 7) * 16;
+                                    *reinterpret_cast<uint4*>(xo_hi + o) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+                                    *reinterpret_cast<uint4*>(xo_lo + o) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+                                }
                             }
                         }
                     }
@@ -544,21 +697,30 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
 
                 // ---------- heads -> Hd[j][row] --------------------------------------------------------
                 {
-                    const uint32_t buf = g_count & 1u;
-                    const uint32_t par0 = (g_count >> 1) & 1u;
+                    const uint32_t par0 = g_count & 1u;
                     ++g_count;
                     if (mtg == 0 && quarter * 32 < T.NHp) {
-                        ptx::mbar_wait(&acc_full[buf * 2u], par0);
+                        ptx::mbar_wait(&acc_full[0], par0);
                         tc::fence_after_sync();
                         if (dbg) dbg[10] = clock64();
-                        const uint32_t tcol = tmem_lane + (buf * 2u) * kSAccCols + (uint32_t)col0;
+                        const uint32_t tcol = tmem_lane + (uint32_t)col0;
                         const float bj = jh < T.NHp ? bias[P.n_hidden * T.Np + jh] : 0.f;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             if (c < nch) {
                                 uint32_t v[8];
                                 tc::tmem_ld8(tcol + c * 8, v);
-                                tc::tmem_wait_ld();
+                                if (TERMS == 3) {
+                                    uint32_t v1[8], v2[8];
+                                    tc::tmem_ld8(tcol + N + c * 8, v1);
+                                    tc::tmem_ld8(tcol + 2 * N + c * 8, v2);
+                                    tc::tmem_wait_ld();
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        v[j] = __float_as_uint(__uint_as_float(v[j]) + (__uint_as_float(v1[j]) + __uint_as_float(v2[j])));
+                                } else {
+                                    tc::tmem_wait_ld();
+                                }
                                 if (jh < T.NHp) {
                                     float4 a, b;
                                     const float sc = 1.0f / (tc::kWScale * tc::kXScale);
@@ -634,17 +796,18 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
     __syncthreads();
     if (warp == 1) {
         __syncwarp();
-        tc::tmem_dealloc(tmem_base, 4 * kSAccCols);
+        tc::tmem_dealloc(tmem_base, 512);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 static int g_tcs_smem = 0;
 
-// rows per tile: the smallest estimated launch time over N = 16, 32, 48, 64.  A step costs about 2500 cycles of serial
-// prologue / final epilogue plus 145 cycles of tensor work per row (3 terms), or the weight stream: `stream_bytes` per
-// step per CTA at min(64 B/clk per SM, 6000 B/clk / active CTAs).
-int tcs_pick_rows(int rows_per_member, int E, int num_sms, long long stream_bytes) {
+// rows per tile: the smallest estimated launch time over N = 16 ... 64.  Per step a CTA spends about 3500 cycles in the
+// serial prologue / final epilogue and, per (K16 block, M tile) of its `pairs` weight blocks, two MMAs of
+// max(N, 32 + N / 2) + max(N / 2, 32 + N / 4) cycles (tools/tc_rate.py); the weight stream bounds it from below at
+// `stream_bytes` / min(64 B/clk per SM, 6000 B/clk over the active CTAs).
+int tcs_pick_rows(int rows_per_member, int E, int num_sms, long long stream_bytes, int pairs) {
     int best = 16;
     double best_cost = 1e30;
     for (int N = 16; N <= kSMaxRows; N += 16) {
@@ -652,7 +815,8 @@ int tcs_pick_rows(int rows_per_member, int E, int num_sms, long long stream_byte
         const int waves = (tiles + num_sms - 1) / num_sms;
         const int active = tiles < num_sms ? tiles : num_sms;
         const double bw = 6000.0 / active < 64.0 ? 6000.0 / active : 64.0;
-        const double compute = 2500.0 + 145.0 * N;
+        const double m1 = N > 32 + N / 2 ? N : 32 + N / 2, m2 = N / 2 > 32 + N / 4 ? N / 2 : 32 + N / 4;
+        const double compute = 3500.0 + pairs * (m1 + m2);
         const double stream = (double)stream_bytes / bw;
         const double cost = waves * (compute > stream ? compute : stream);
         if (cost < best_cost - 1e-9) { best_cost = cost; best = N; }
@@ -661,7 +825,7 @@ int tcs_pick_rows(int rows_per_member, int E, int num_sms, long long stream_byte
 }
 
 cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long long wimg_member_stride, int terms, int kps,
-                               int rows_override, int num_sms, cudaStream_t stream, const char** name, long long* dbg) {
+                               int rows_override, int skew, int num_sms, cudaStream_t stream, const char** name, long long* dbg) {
     TcsParams T{};
     T.dbg = dbg;
     T.wimg = wimg;
@@ -673,9 +837,13 @@ cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long 
     T.Kcap = max(T.Np, T.nkb0 * 16);
     T.terms = terms;
     T.kps = kps;
+    T.skew = skew & 0xfffff;
+    T.debug = (skew >> 20) & 0xff;
+    const bool generic = (skew >> 28) & 1;     // diagnostic: force the table-driven MMA schedule
     T.nmt = T.Np > 128 ? 2 : 1;
     if (T.Np > 256 || T.NHp > 128 || kps < 1 || kps > kSMaxKps) return cudaErrorInvalidConfiguration;
-    int N = rows_override > 0 ? rows_override : tcs_pick_rows(P.rows_per_member, P.E, num_sms, wimg_member_stride);
+    const int pairs = T.nkb0 * T.nmt + (P.n_hidden - 1) * T.nkbH * T.nmt + T.nkbH;   // (K16 block, M tile) pairs per step
+    int N = rows_override > 0 ? rows_override : tcs_pick_rows(P.rows_per_member, P.E, num_sms, wimg_member_stride, pairs);
     N = min(kSMaxRows, max(16, round_up(N, 16)));
     int tiles = (P.rows_per_member + N - 1) / N;
     N = min(N, round_up((P.rows_per_member + tiles - 1) / tiles, 16));      // balance the rows over the tiles
@@ -690,14 +858,61 @@ cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long 
     const TcsSmem L = tcs_smem_layout(N, P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, T.Kcap, kps, stages);
     if (L.total > 226 * 1024) return cudaErrorInvalidConfiguration;
     T.R = P;
+    // The stage table of one horizon step, in weight-stream order: GEMM g, M tile mt, K blocks [s0, s0 + kbs).  Two 16-byte
+    // words per stage, everything the MMA thread needs precomputed:
+    //   e0 = { flags, bytes in the weight image, X offset (16-byte units: input buffer g & 1, K block s0), TMEM column of the
+    //          M tile's accumulator }          e1 = { R, kbs, accumulate (s0 > 0), g }
+    //   flags: 1 wait xr[0] first (first stage of the GEMM), 2 wait xr[1] first (first stage that needs a K block produced
+    //          by the M-tile-1 warps), 4 commit acc_full[mt] after, 8 last stage of the GEMM, 16 M tile 1
+    {
+        int n = 0;
+        for (int g = 0; g <= P.n_hidden; ++g) {
+            const int nkb = g == 0 ? T.nkb0 : T.nkbH;
+            const int Npad = g == P.n_hidden ? T.NHp : T.Np;
+            const int nmt = (Npad + 127) >> 7;
+            const int kb_split = (g == 0 || T.nmt == 1) ? 0 : 8;       // the prologue spreads layer 0 over all warps
+            bool w1 = false;
+            for (int mt = 0; mt < nmt; ++mt) {
+                const int R = std::min(128, Npad - 128 * mt);
+                for (int s0 = 0; s0 < nkb; s0 += kps) {
+                    const int kbs = std::min(kps, nkb - s0);
+                    const bool last = mt == nmt - 1 && s0 + kbs >= nkb;
+                    uint32_t flags = mt ? 16u : 0u;
+                    if (mt == 0 && s0 == 0) flags |= 1u;
+                    if (!w1 && (s0 + kbs > kb_split || last)) { flags |= 2u; w1 = true; }
+                    if (s0 + kbs >= nkb) flags |= 4u;
+                    if (last) flags |= 8u;
+                    if (n >= kSMaxEnt) return cudaErrorInvalidConfiguration;
+                    T.tab[2 * n] = make_uint4(flags, (uint32_t)kbs * 64u * (uint32_t)R,
+                                              (uint32_t)(g & 1) * ((uint32_t)(2 * L.xbytes) >> 4) + (uint32_t)s0 * 16u, (uint32_t)mt * kSAccStride);
+                    T.tab[2 * n + 1] = make_uint4((uint32_t)R, (uint32_t)kbs, s0 > 0 ? 1u : 0u, (uint32_t)g);
+                    ++n;
+                }
+            }
+        }
+        T.nent = n;
+    }
     if ((int)L.total > g_tcs_smem) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        cudaError_t e = cudaSuccess;
+        auto set = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); };
+        set((const void*)rollout_tcs_kernel<3, 0, 0>); set((const void*)rollout_tcs_kernel<1, 0, 0>);
+        set((const void*)rollout_tcs_kernel<3, 2, 48>); set((const void*)rollout_tcs_kernel<1, 2, 48>);
+        set((const void*)rollout_tcs_kernel<3, 3, 48>); set((const void*)rollout_tcs_kernel<1, 3, 48>);
+        set((const void*)rollout_tcs_kernel<3, 3, 64>); set((const void*)rollout_tcs_kernel<1, 3, 64>);
         if (e != cudaSuccess) return e;
         g_tcs_smem = (int)L.total;
     }
     if (name) *name = terms == 3 ? "rollout_tcs_kernel(swapped operands, fp16 hi/lo x3)" : "rollout_tcs_kernel(swapped operands, f16 x1)";
     const int grid = min(T.total_tiles, num_sms);
-    rollout_tcs_kernel<<<grid, kSThreads, L.total, stream>>>(T);
+    // compile-time MMA schedule for the reference architecture, table-driven otherwise
+    const bool spec = !generic && P.n_hidden == 4 && T.Np == 208 && kps == 4 && (T.nkb0 == 2 || T.nkb0 == 3) && (T.NHp == 48 || T.NHp == 64) &&
+                      !(T.nkb0 == 2 && T.NHp == 64);
+#define CADM_TCS_LAUNCH(TE, K0, HP) rollout_tcs_kernel<TE, K0, HP><<<grid, kSThreads, L.total, stream>>>(T)
+    if (!spec) { if (terms == 3) CADM_TCS_LAUNCH(3, 0, 0); else CADM_TCS_LAUNCH(1, 0, 0); }
+    else if (T.nkb0 == 2) { if (terms == 3) CADM_TCS_LAUNCH(3, 2, 48); else CADM_TCS_LAUNCH(1, 2, 48); }
+    else if (T.NHp == 48) { if (terms == 3) CADM_TCS_LAUNCH(3, 3, 48); else CADM_TCS_LAUNCH(1, 3, 48); }
+    else { if (terms == 3) CADM_TCS_LAUNCH(3, 3, 64); else CADM_TCS_LAUNCH(1, 3, 64); }
+#undef CADM_TCS_LAUNCH
     return cudaGetLastError();
 }
 
@@ -714,7 +929,7 @@ __global__ void __launch_bounds__(128, 1) tcs_gemm_selftest_kernel(const float* 
     const int xsbo = (Kcap / 8) * 128;
     const int xbytes = (rows / 8) * xsbo;
     unsigned char* xhi = smem;
-    unsigned char* xlo = smem + xbytes;
+    unsigned char* xlo = smem + xbytes;                 // directly behind X_hi: [X_hi ; X_lo] is one B operand of 2 x rows
     unsigned char* wst = smem + (2 * xbytes + 127) / 128 * 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(wst + kps * 8192);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
@@ -726,7 +941,7 @@ __global__ void __launch_bounds__(128, 1) tcs_gemm_selftest_kernel(const float* 
     }
     if (warp == 1) {
         __syncwarp();
-        tc::tmem_alloc(tmem_slot, 128);
+        tc::tmem_alloc(tmem_slot, 512);
         tc::tmem_relinquish();
     }
     for (int i = tid; i < Kcap * (rows / 8); i += 128) {
@@ -742,26 +957,34 @@ __global__ void __launch_bounds__(128, 1) tcs_gemm_selftest_kernel(const float* 
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const int nmt = (Npad + 127) >> 7;
-    if (tid == 0) {
-        const uint32_t xhi_a = ptx::smem_u32(xhi), xlo_a = ptx::smem_u32(xlo), w_a = ptx::smem_u32(wst);
-        uint32_t ph = 0;
-        size_t off = 0;
-        for (int mt = 0; mt < nmt; ++mt) {
-            const int R = min(128, Npad - 128 * mt);
-            for (int s0 = 0; s0 < nkb; s0 += kps) {
-                const int kbs = min(kps, nkb - s0);
-                const uint32_t bytes = (uint32_t)kbs * 64u * (uint32_t)R;
-                ptx::mbar_arrive_expect_tx(&bars[0], bytes);
-                ptx::bulk_g2s(wst, wimg + off, bytes, &bars[0]);
-                off += bytes;
-                ptx::mbar_wait(&bars[0], ph);
-                tc::fence_after_sync();
-                tcs::issue_stage(tmem_base + mt * kSAccCols, w_a, R, kbs, s0, xhi_a, xlo_a, (uint32_t)xsbo, tcs::idesc((uint32_t)rows), terms);
-                tc::mma_commit(&bars[1]);
-                ptx::mbar_wait(&bars[1], ph);          // serialise: the single weight slot is reused
-                ph ^= 1u;
+    if (warp == 0) {
+        if (ptx::elect_one()) {
+            const uint32_t xhi_d = ptx::smem_u32(xhi) >> 4, w_a = ptx::smem_u32(wst);
+            uint32_t ph = 0;
+            size_t off = 0;
+            for (int mt = 0; mt < nmt; ++mt) {
+                const int R = min(128, Npad - 128 * mt);
+                for (int s0 = 0; s0 < nkb; s0 += kps) {
+                    const int kbs = min(kps, nkb - s0);
+                    const uint32_t bytes = (uint32_t)kbs * 64u * (uint32_t)R;
+                    ptx::mbar_arrive_expect_tx(&bars[0], bytes);
+                    ptx::bulk_g2s(wst, wimg + off, bytes, &bars[0]);
+                    off += bytes;
+                    ptx::mbar_wait(&bars[0], ph);
+                    tc::fence_after_sync();
+                    if (terms == 3)
+                        tcs::issue_stage<3>(tmem_base + mt * kSAccStride, w_a >> 4, (uint32_t)R, kbs, s0 > 0 ? 1u : 0u, xhi_d + s0 * 16u,
+                                            (uint32_t)rows, (uint32_t)xsbo);
+                    else
+                        tcs::issue_stage<1>(tmem_base + mt * kSAccStride, w_a >> 4, (uint32_t)R, kbs, s0 > 0 ? 1u : 0u, xhi_d + s0 * 16u,
+                                            (uint32_t)rows, (uint32_t)xsbo);
+                    tc::mma_commit(&bars[1]);
+                    ptx::mbar_wait(&bars[1], ph);          // serialise: the single weight slot is reused
+                    ph ^= 1u;
+                }
             }
         }
+        __syncwarp();
     }
     __syncthreads();
     tc::fence_after_sync();
@@ -769,12 +992,18 @@ __global__ void __launch_bounds__(128, 1) tcs_gemm_selftest_kernel(const float* 
     for (int mt = 0; mt < nmt; ++mt) {
         const int j = mt * 128 + tid;
         for (int c = 0; c < rows; c += 8) {
-            uint32_t v[8];
-            tc::tmem_ld8(tl + mt * kSAccCols + c, v);
+            uint32_t v[8], v1[8], v2[8];
+            tc::tmem_ld8(tl + mt * kSAccStride + c, v);
+            tc::tmem_ld8(tl + mt * kSAccStride + rows + c, v1);
+            tc::tmem_ld8(tl + mt * kSAccStride + 2 * rows + c, v2);
             tc::tmem_wait_ld();
             if (j < Nout) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) out[(size_t)(c + q) * Nout + j] = __uint_as_float(v[q]) * (1.0f / (tc::kWScale * tc::kXScale));
+                for (int q = 0; q < 8; ++q) {
+                    float acc = __uint_as_float(v[q]);
+                    if (terms == 3) acc += __uint_as_float(v1[q]) + __uint_as_float(v2[q]);
+                    out[(size_t)(c + q) * Nout + j] = acc * (1.0f / (tc::kWScale * tc::kXScale));
+                }
             }
         }
     }
@@ -782,7 +1011,7 @@ __global__ void __launch_bounds__(128, 1) tcs_gemm_selftest_kernel(const float* 
     __syncthreads();
     if (warp == 1) {
         __syncwarp();
-        tc::tmem_dealloc(tmem_base, 128);
+        tc::tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -794,6 +1023,114 @@ cudaError_t launch_tcs_gemm_selftest(const float* X, const unsigned char* wimg, 
     cudaError_t e = cudaFuncSetAttribute(tcs_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     tcs_gemm_selftest_kernel<<<1, 128, smem_bytes, stream>>>(X, wimg, rows, K, Nout, kps, terms, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Micro-benchmark of the swapped kernel's MMA stream in isolation: one elected thread issues `iters` rounds of 4 weight
+// stages (kps K16 blocks each, R weight rows, 2 MMAs per block as in rollout_tcs_kernel<3>) on resident shared memory.
+// mode bit 0: a second thread streams bulk copies INTO the ring slots while they are read (the real kernel's traffic);
+// mode bit 1: alternate the two accumulator regions per round; mode bit 2: 16 epilogue-like warps hammer shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSThreads, 1) tcs_mma_rate_kernel(int rows, int iters, int R, int kps, int mode,
+                                                                    const unsigned char* src, long long* cycles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int xsbo = (208 / 8) * 128;
+    const int xbytes = (rows / 8) * xsbo;
+    unsigned char* xb = smem;
+    unsigned char* ring = smem + (4 * xbytes + 127) / 128 * 128;
+    const int slot_bytes = kps * 8192;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 4 * slot_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    volatile uint32_t* stop = reinterpret_cast<volatile uint32_t*>(bars + 7);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (4 * xbytes + 4 * slot_bytes + 128) / 4; i += kSThreads) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) {
+        for (int i = 0; i < 7; ++i) ptx::mbar_init(&bars[i], 1);
+        *stop = 0u;
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_alloc(tmem_slot, 512);
+        tc::tmem_relinquish();
+    }
+    ptx::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 1) {
+        if (ptx::elect_one()) {
+            const uint32_t x16 = ptx::smem_u32(xb) >> 4, w16 = ptx::smem_u32(ring) >> 4;
+            const long long t0 = clock64();
+            for (int it = 0; it < iters; ++it) {
+                const uint32_t d = tmem_base + ((mode & 2) ? (uint32_t)(it & 1) * kSAccStride : 0u);
+                for (int sl = 0; sl < 4; ++sl) {
+                    tcs::issue_stage<3>(d, w16 + (uint32_t)sl * ((uint32_t)slot_bytes >> 4), (uint32_t)R, kps, sl > 0 ? 1u : 0u,
+                                        x16 + (uint32_t)((sl * kps) % 13) * 16u, (uint32_t)rows, (uint32_t)xsbo);
+                    tc::mma_commit(&bars[1]);
+                }
+            }
+            const long long t1 = clock64();
+            tc::mma_commit(&bars[0]);
+            ptx::mbar_wait(&bars[0], 0);
+            const long long t2 = clock64();
+            if (blockIdx.x == 0) {
+                cycles[0] = t1 - t0;
+                cycles[1] = t2 - t0;
+            }
+            *stop = 1u;
+        }
+        __syncwarp();
+    } else if (warp == 0 && (mode & 1)) {
+        if (tid == 0) {
+            uint32_t ph[4] = {0u, 0u, 0u, 0u};
+            long long n = 0;
+            const uint32_t bytes = (uint32_t)kps * 64u * (uint32_t)R;
+            for (int i = 0; i < 4; ++i) {
+                ptx::mbar_arrive_expect_tx(&bars[2 + i], bytes);
+                ptx::bulk_g2s(ring + i * slot_bytes, src + ((n++ * 32768) & 0xfffff), bytes, &bars[2 + i]);
+            }
+            while (!*stop) {
+                for (int i = 0; i < 4; ++i) {
+                    ptx::mbar_wait(&bars[2 + i], ph[i]);
+                    ph[i] ^= 1u;
+                    ptx::mbar_arrive_expect_tx(&bars[2 + i], bytes);
+                    ptx::bulk_g2s(ring + i * slot_bytes, src + ((n++ * 32768) & 0xfffff), bytes, &bars[2 + i]);
+                }
+            }
+            for (int i = 0; i < 4; ++i) ptx::mbar_wait(&bars[2 + i], ph[i]);
+            if (blockIdx.x == 0) cycles[2] = n * bytes;
+        }
+    } else if (warp >= 2 && (mode & 4)) {
+        // epilogue-like traffic: TMEM loads + 16-byte shared-memory stores into the second X buffer
+        const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        unsigned char* dst = xb + 2 * xbytes;
+        const int lane = tid & 31;
+        while (!*stop) {
+            uint32_t v[8];
+            tc::tmem_ld8(tl + 8 * (warp & 7), v);
+            tc::tmem_wait_ld();
+            *reinterpret_cast<uint4*>(dst + ((warp - 2) & 3) * xsbo + lane * 16) = make_uint4(v[0], v[1], v[2], v[3]);
+            __nanosleep(100);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+cudaError_t launch_tcs_mma_rate(int rows, int iters, int R, int kps, int mode, const unsigned char* src, long long* cycles,
+                                cudaStream_t stream) {
+    const int xbytes = (rows / 8) * (208 / 8) * 128;
+    const int smem_bytes = (4 * xbytes + 127) / 128 * 128 + 4 * kps * 8192 + 256;
+    cudaError_t e = cudaFuncSetAttribute(tcs_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    tcs_mma_rate_kernel<<<(mode & 8) ? 148 : ((mode & 16) ? 74 : 1), kSThreads, smem_bytes, stream>>>(rows, iters, R, kps, mode, src, cycles);
     return cudaGetLastError();
 }
 

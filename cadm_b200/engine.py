@@ -93,7 +93,8 @@ class PlannerEngine:
             ccfg = cfg.to_c()
             check(None, self.lib.cadm_plan_create(C.byref(ccfg), C.byref(self._h)))
         # tuning knobs of the tensor-core path (diagnostics / sweeps; the defaults are what bench.py measures)
-        for opt, env in (("tc_variant", "CADM_TC_VARIANT"), ("tcs_rows", "CADM_TCS_ROWS"), ("tcs_kps", "CADM_TCS_KPS")):
+        for opt, env in (("tc_variant", "CADM_TC_VARIANT"), ("tcs_rows", "CADM_TCS_ROWS"), ("tcs_kps", "CADM_TCS_KPS"),
+                         ("tcs_skew", "CADM_TCS_SKEW")):
             if os.environ.get(env):
                 self.set_option(opt, int(os.environ[env]))
         self.In = cfg.proc_obs_dim + cfg.act_dim + cfg.ctx_dim

@@ -193,7 +193,9 @@ int cadm_selftest_tcs_gemm(const float* X, const float* W, int32_t rows, int32_t
 /* Tuning knobs of the tensor-core path (the defaults are what bench.py measures):
  *   "tc_variant"  0 = pick by batch size, 1 = 128-row tiles (rollout_tc.cu), 2 = swapped operands (rollout_tcs.cu)
  *   "tcs_rows"    rows per tile of the swapped kernel: 0 = pick, else 16 / 32 / 48 / 64
- *   "tcs_kps"     K16 blocks per weight stage of the swapped kernel's image, 1..4 (before cadm_plan_set_weights) */
+ *   "tcs_kps"     K16 blocks per weight stage of the swapped kernel's image, 1..4 (before cadm_plan_set_weights)
+ *   "tcs_skew"    start-delay step in cycles that de-phases the CTAs of the swapped kernel (0 = off)
+ *   "trace"       1 = record the clock64 phase trace of CTA 0 (cadm_debug_trace); slows that CTA down */
 int cadm_set_option(void* handle, const char* name, int32_t value);
 
 /* Diagnostic micro-benchmark: n_mma back-to-back tcgen05.mma (M=128, N, K=16, fp16) on resident shared-memory operands,
@@ -203,6 +205,12 @@ int cadm_set_option(void* handle, const char* name, int32_t value);
  * 6 MMAs.  cycles_host[0] = issue time, [1] = time until the commit is observed (clock64), [2] = 8 KB copies completed. */
 int cadm_selftest_tc_rate(int32_t N, int32_t n_mma, int32_t a_lbo, int32_t n_acc, int32_t swapped, int32_t background,
                           int64_t* cycles_host);
+
+/* Diagnostic micro-benchmark of the swapped kernel's MMA stream: `iters` rounds of 4 weight stages (kps K16 blocks of R
+ * weight rows each, 2 MMAs per block) issued by one elected thread; mode bit 0 = bulk copies stream into the ring slots
+ * meanwhile, bit 1 = alternate accumulators, bit 2 = epilogue-like TMEM / shared-memory traffic from 16 warps.
+ * cycles_host[0] = issue time, [1] = completion time (clock64), [2] = bytes streamed. */
+int cadm_selftest_tcs_rate(int32_t rows, int32_t iters, int32_t R, int32_t kps, int32_t mode, int64_t* cycles_host);
 
 /* Diagnostic: clock64 trace of CTA 0 of the last tensor-core rollout launched with timing enabled, [step][32] slots
  * (see rollout_tc.cu); copies `count` int64 values to the host.  Synchronises. */

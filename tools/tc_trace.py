@@ -12,6 +12,7 @@ eng = model.engine
 for _ in range(3):
     eng.plan_cem(inp["obs"], inp["init_mean"], inp["init_var"], seed=1, logs=False)
 eng.set_timing(True)
+eng.set_option("trace", 1)
 eng.plan_cem(inp["obs"], inp["init_mean"], inp["init_var"], seed=2, logs=False)
 tr = eng.debug_trace(30)
 print("rollout ms (5 launches):", eng.last_rollout_ms())
