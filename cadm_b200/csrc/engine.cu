@@ -151,10 +151,11 @@ int run_rollout(Engine* E, RolloutParams& P, cudaStream_t s) {
             P.bpack = E->bpack_tc;
             P.bias_stride = E->bias_stride_tc;
             {
-                // small batches (fewer 128-row tiles than ~3/4 of the SMs) go to the swapped-operand kernel
-                const int tiles128 = P.E * ((P.rows_per_member + 127) / 128);
+                // batches whose 64-row tiles fit the SMs in one wave go to the swapped-operand kernel (it spreads them over
+                // 2-4x more SMs than 128-row tiles); larger ones keep the 128-row tiles of rollout_tc.cu
+                const int tiles64 = P.E * ((P.rows_per_member + 63) / 64);
                 const bool swapped_ok = E->Np16 <= 256 && E->NHp16 <= 128;
-                const bool swapped = E->tc_variant == 2 || (E->tc_variant == 0 && swapped_ok && 4 * tiles128 < 3 * E->num_sms);
+                const bool swapped = E->tc_variant == 2 || (E->tc_variant == 0 && swapped_ok && tiles64 <= E->num_sms);
                 const int terms = E->precision == CADM_PREC_TC_3X ? 3 : 1;
                 if (swapped)
                     CU(E, launch_rollout_tcs(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_kps, E->tcs_rows, E->tcs_skew, E->num_sms, s,

@@ -48,7 +48,7 @@ constexpr int kSMaxKps = 4;
 constexpr int kSMaxEnt = 96;                   // stage-table entries per step
 
 struct TcsSmem {
-    size_t off_x, off_w, off_s, off_hd, off_bias, off_vec, off_rowi, off_feat, off_zero, off_act, off_ctx, off_tab, off_bar, total;
+    size_t off_x, off_w, off_s, off_hd, off_bias, off_vec, off_rowi, off_feat, off_zero, off_act, off_ctx, off_nz, off_tab, off_bar, total;
     int xbytes, slot_bytes;
 };
 
@@ -61,7 +61,7 @@ __host__ __device__ inline TcsSmem tcs_smem_layout(int N, int D, int A, int C, i
     L.off_x = o; o += (size_t)4 * L.xbytes;      // two buffers x [hi | lo]
     o = (o + 127) / 128 * 128;
     L.off_w = o; o += (size_t)stages * L.slot_bytes;
-    L.off_s = o; o += (size_t)round_up(N * (D + 1), 4) * 4;
+    L.off_s = o; o += (size_t)round_up(N * (D + 3), 4) * 4;          // state rows: D values, pad, sin / cos of the angle
     L.off_hd = o; o += (size_t)NHp * N * 4;
     o = (o + 15) / 16 * 16;
     L.off_bias = o; o += (size_t)round_up(n_hidden * Np + NHp, 4) * 4;
@@ -71,6 +71,7 @@ __host__ __device__ inline TcsSmem tcs_smem_layout(int N, int D, int A, int C, i
     L.off_zero = o; o += 16;
     L.off_act = o; o += (size_t)2 * N * A * 4;
     L.off_ctx = o; o += (size_t)N * (C > 0 ? C : 1) * 4;
+    L.off_nz = o; o += (size_t)N * ((D + 3) / 4 * 4) * 4;           // this step's N(0,1) draws, [row][4 * blocks]
     o = (o + 15) / 16 * 16;
     L.off_tab = o; o += (size_t)kSMaxEnt * 32;                        // stage table (copied from the kernel parameters)
     L.off_bar = o; o += (size_t)(2 * kSMaxStages + 2 + 2 + 4) * 8;   // w_full, w_empty, xr[2], acc_full[2], tmem slot
@@ -152,7 +153,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // The MMAs of one weight stage (KBS K16 blocks of one M tile), fully unrolled, descriptors advanced by constant adds.
-// TERMS == 3: per block  D[0, 2 rows) (+)= W_hi [X_hi ; X_lo]  (one MMA with N = 2 rows)  and  D[2 rows, 3 rows) (+)= W_lo X_hi;
+// TERMS == 3: per block  D[0, 2 rows) (+)= W_hi [X_hi ; X_lo]  (one MMA with N = 2 rows)  and then  D[0, rows) += W_lo X_hi;
 // TERMS == 1: D[0, rows) (+)= W_hi X_hi.   a_hi / a_lo / b are complete 64-bit shared-memory descriptors of the first block.
 template <int TERMS, int KBS>
 __device__ __forceinline__ void issue_blocks(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b, uint32_t a_step, uint32_t rows,
@@ -161,8 +162,8 @@ __device__ __forceinline__ void issue_blocks(uint32_t d_tmem, uint64_t a_hi, uin
     for (int j = 0; j < KBS; ++j) {
         const uint32_t acc = j == 0 ? accum : 1u;
         if (TERMS == 3) {
-            tc::mma_f16_ss(d_tmem, a_hi, b, idesc2, acc);                   // W_hi [X_hi ; X_lo]
-            tc::mma_f16_ss(d_tmem + 2u * rows, a_lo, b, idesc1, acc);       // W_lo X_hi
+            tc::mma_f16_ss(d_tmem, a_hi, b, idesc2, acc);                   // D[0, 2 rows) (+)= W_hi [X_hi ; X_lo]
+            tc::mma_f16_ss(d_tmem, a_lo, b, idesc1, 1u);                    // D[0, rows)    += W_lo X_hi
         } else {
             tc::mma_f16_ss(d_tmem, a_hi, b, idesc1, acc);
         }
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
     float2* feat_f = reinterpret_cast<float2*>(smem + L.off_feat + 96 * 16);
     float* act_s = reinterpret_cast<float*>(smem + L.off_act);
     float* ctx_s = reinterpret_cast<float*>(smem + L.off_ctx);
+    float* nz_s = reinterpret_cast<float*>(smem + L.off_nz);
     uint4* tab = reinterpret_cast<uint4*>(smem + L.off_tab);
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* w_empty = w_full + kSMaxStages;
@@ -313,8 +315,8 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
     const int xsbo = (T.Kcap / 8) * 128;
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
-        ptx::mbar_init(&xr[0], 8);
-        ptx::mbar_init(&xr[1], 8);
+        ptx::mbar_init(&xr[0], 16);
+        ptx::mbar_init(&xr[1], 16);
         ptx::mbar_init(&acc_full[0], 1);
         ptx::mbar_init(&acc_full[1], 1);
         done[0] = 0u;
@@ -492,12 +494,9 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
         const int et = tid - 64;                       // 0..511
         const int ew = warp - 2;                       // 0..15
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-        const int mtg = ew >> 3;                       // M tile this warp serves
-        const int cslice = (ew >> 2) & 1;              // column (row-of-the-batch) half
+        const int cslice = ew >> 2;                    // the warp takes the 8-column (8 batch rows) chunks cslice, cslice + 4, ...
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const int jh = mtg * 128 + quarter * 32 + lane;                 // hidden unit (TMEM lane of M tile mtg)
-        const int nch = N >> 4;                        // 8-column chunks per column slice (N / 2 / 8)
-        const int col0 = cslice * (N >> 1);
+        const int nchunks = N >> 3;
         uint32_t g_count = 0;                          // GEMMs so far   = completions of acc_full[0]
         uint32_t c1cnt = 0;                            // 2-tile GEMMs   = completions of acc_full[1]
         unsigned char* const x0hi = xbuf;              // layer-input buffer 0 (layer 0 and every other layer after it)
@@ -522,12 +521,12 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 int idx = k;
                 if (P.env_id == CADM_ENV_HALFCHEETAH) {          // [o1, sin o2, cos o2, o3:]
                     if (k == 0) idx = 1;
-                    else if (k == 1) { idx = 2; flags = 2; }
-                    else if (k == 2) { idx = 2; flags = 4; }
+                    else if (k == 1) idx = D + 1;                 // sin o2, kept beside the state (computed once per step)
+                    else if (k == 2) idx = D + 2;                 // cos o2
                 } else if (P.env_id == CADM_ENV_ANT) {
                     idx = k + 1;                                  // o[1:]
                 }
-                base = (int)L.off_s + idx * 4; stride = (D + 1) * 4;
+                base = (int)L.off_s + idx * 4; stride = (D + 3) * 4;
                 mean = P.obs_mean[k]; inv = 1.0f / (P.obs_std[k] + 1e-10f);
             } else if (k < P.P + A) {
                 const int ai = k - P.P;
@@ -575,7 +574,7 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 const int r = i / D, d = i - r * D;
                 float v = 0.f;
                 if (r < nrows) v = (P.row_mode == kRowsPlanner) ? P.obs0[r_mi[r] * D + d] : P.obs0[(size_t)r_src[r] * D + d];
-                S[r * (D + 1) + d] = v;
+                S[r * (D + 3) + d] = v;
             }
             for (int i = et; i < N * P.C; i += kSEpiThreads) {
                 const int r = i / P.C, c = i - r * P.C;
@@ -592,6 +591,7 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
             };
             for (int i = et; i < 2 * N * A; i += kSEpiThreads) act_s[i] = 0.f;   // rows >= nrows stay finite
             ptx::bar_sync(1, kSEpiThreads);
+            if (P.env_id == CADM_ENV_HALFCHEETAH && et < N) sincosf(S[et * (D + 3) + 2], &S[et * (D + 3) + D + 1], &S[et * (D + 3) + D + 2]);
             prefetch_actions(0);
             tcs::cp_async_wait_all();
             ptx::bar_sync(1, kSEpiThreads);
@@ -601,10 +601,9 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
             for (int t = 0; t < P.h; ++t) {
                 long long* dbg = (T.dbg && blockIdx.x == 0 && ew == 2 && lane == 0 && tile == (int)blockIdx.x && t < 64) ? T.dbg + t * 64 : nullptr;
                 if (dbg) dbg[0] = clock64();
-                if (t + 1 < P.h) prefetch_actions(t + 1);                            // lands during this step
                 // ---------- prologue: reward of the current state; layer-0 input ------------------------
                 if (et < nrows) {
-                    const float* s = S + et * (D + 1);
+                    const float* s = S + et * (D + 3);
                     const float* arow = act_s + (t & 1) * N * A + et * A;
                     if (env_reward_reads_next(P.env_id)) {
                         if (t > 0) ret += env_reward_next(P.env_id, s);
@@ -612,6 +611,7 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                         ret += env_reward_current(P.env_id, s, arow, A, P.max_torque);
                     }
                 }
+                if (dbg) dbg[13] = clock64();
                 {
                     const int par_off = (t & 1) * N * A * 4;
                     const bool onehot_mode = P.discrete && P.row_mode == kRowsPlanner;
@@ -624,11 +624,6 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                         for (int jj = 0; jj < 8; ++jj) {
                             const int r = rg * 8 + jj;
                             float src = *reinterpret_cast<const float*>(smem + fi.x + r * fi.y + ((fi.z & 1) ? par_off : 0));
-                            if (fi.z & 6) {
-                                float sn, cs;
-                                sincosf(src, &sn, &cs);
-                                src = (fi.z & 2) ? sn : cs;
-                            }
                             if (onehot_mode && (fi.z & 1)) {
                                 const int oh = r < nrows ? __ldg(P.actions_int + (size_t)r_src[r] * P.h + t) : -1;
                                 src = (oh == k - P.P) ? 1.f : 0.f;
@@ -637,101 +632,119 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                         }
                         tcs::store_rows8(x0hi, x0hi + L.xbytes, xsbo, rg, k, y);
                     }
+                    if (dbg) dbg[14] = clock64();
                     ptx::fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&xr[mtg]);
+                    if (lane == 0) { ptx::mbar_arrive(&xr[0]); ptx::mbar_arrive(&xr[1]); }
                 }
                 if (dbg) dbg[1] = clock64();
                 // ---------- hidden layers: accumulator -> bias + swish -> next layer's B operand ----------
 #pragma unroll 1
                 for (int l = 0; l < P.n_hidden; ++l) {
-                    const int my_mt = mtg < T.nmt ? mtg : T.nmt - 1;
-                    ptx::mbar_wait(&acc_full[my_mt], (my_mt ? c1cnt : g_count) & 1u);
+                    // GEMM l read buffer l & 1; its output (the input of GEMM l + 1) goes to the other buffer
+                    unsigned char* const xo_hi = xbuf + ((l + 1) & 1) * 2 * L.xbytes;
+                    unsigned char* const xo_lo = xo_hi + L.xbytes;
+                    // All 16 warps take each M tile in turn (quarter = TMEM lane quarter, cslice = column chunks): tile 0's
+                    // epilogue runs under tile 1's MMAs, tile 1's under the next layer's first K blocks.
+#pragma unroll 1
+                    for (int mt = 0; mt < 2; ++mt) {
+                        if (mt < T.nmt) {
+                            ptx::mbar_wait(&acc_full[mt], (mt ? c1cnt : g_count) & 1u);
+                            tc::fence_after_sync();
+                            if (dbg && l < 4 && mt == 0) dbg[2 + 2 * l] = clock64();
+                            const int jh = mt * 128 + quarter * 32 + lane;          // hidden unit = TMEM lane of M tile mt
+                            if (mt * 128 + quarter * 32 < T.Np && !(T.debug & 2)) {
+                                const uint32_t tcol = tmem_lane + (uint32_t)mt * kSAccStride;
+                                const float b8 = jh < T.Np ? bias[l * T.Np + jh] : 0.f;
+                                for (int c = cslice; c < nchunks; c += 4) {
+                                    uint32_t v[8];
+                                    tc::tmem_ld8(tcol + c * 8, v);
+                                    if (TERMS == 3) {
+                                        uint32_t v1[8];
+                                        tc::tmem_ld8(tcol + N + c * 8, v1);
+                                        tc::tmem_wait_ld();
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v1[j]));
+                                    } else {
+                                        tc::tmem_wait_ld();
+                                    }
+                                    float y[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) y[j] = tc::swish8_fast(fmaf(__uint_as_float(v[j]), 1.0f / tc::kWScale, b8));
+                                    if (jh < T.Np) {
+                                        uint32_t hq[4], lq[4];
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) tc::split2(y[2 * j], y[2 * j + 1], hq[j], lq[j]);
+                                        const int o = c * xsbo + (jh >> 3) * 128 + (jh & 7) * 16;
+                                        *reinterpret_cast<uint4*>(xo_hi + o) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+                                        *reinterpret_cast<uint4*>(xo_lo + o) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+                                    }
+                                }
+                            }
+                            tc::fence_before_sync();
+                            ptx::fence_proxy_async();
+                        }
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&xr[mt]);
+                        if (dbg && l < 4 && mt == 0) dbg[3 + 2 * l] = clock64();
+                    }
                     ++g_count;
                     if (T.nmt == 2) ++c1cnt;
-                    tc::fence_after_sync();
-                    if (dbg && l < 4) dbg[2 + 2 * l] = clock64();
-                    if (mtg < T.nmt && (mtg * 128 + quarter * 32) < T.Np && !(T.debug & 2)) {
-                        // GEMM l read buffer l & 1; its output (the input of GEMM l + 1) goes to the other buffer
-                        unsigned char* const xo_hi = xbuf + ((l + 1) & 1) * 2 * L.xbytes;
-                        unsigned char* const xo_lo = xo_hi + L.xbytes;
-                        const uint32_t tcol = tmem_lane + (uint32_t)mtg * kSAccStride + (uint32_t)col0;
-                        const float b8 = jh < T.Np ? bias[l * T.Np + jh] : 0.f;
-                        const int rg0 = col0 >> 3;
+                    // ---------- off the critical path: the warps are idle from here until the next layer's first accumulator is
+                    // ready: next step's actions, this step's noise
+                    if (l == 0) {
+                        if (t + 1 < P.h) prefetch_actions(t + 1);
+                        if (!P.deterministic) {
+                            for (int i = et; i < N * nj; i += kSEpiThreads) {
+                                const int jb = i / N, r = i - jb * N;
+                                float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                                if (r < nrows) {
+                                    if (P.eps != nullptr) {
+                                        const float* ep = P.eps + (P.row_mode == kRowsPlanner ? (size_t)t * eps_step_stride : 0) + (size_t)r_eps[r] * D;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (c < nch) {
-                                uint32_t v[8];
-                                tc::tmem_ld8(tcol + c * 8, v);
-                                if (TERMS == 3) {
-                                    uint32_t v1[8], v2[8];
-                                    tc::tmem_ld8(tcol + N + c * 8, v1);
-                                    tc::tmem_ld8(tcol + 2 * N + c * 8, v2);
-                                    tc::tmem_wait_ld();
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j)
-                                        v[j] = __float_as_uint(__uint_as_float(v[j]) + (__uint_as_float(v1[j]) + __uint_as_float(v2[j])));
-                                } else {
-                                    tc::tmem_wait_ld();
+                                        for (int ii = 0; ii < 4; ++ii) nz[ii] = 4 * jb + ii < D ? __ldg(ep + 4 * jb + ii) : 0.f;
+                                    } else {
+                                        normal4_fast(P.seed, (uint32_t)jb, (uint32_t)r_rid[r], (uint32_t)t, (uint32_t)P.it, nz);
+                                    }
                                 }
-                                float y[8];
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) y[j] = tc::swish8_fast(fmaf(__uint_as_float(v[j]), 1.0f / tc::kWScale, b8));
-                                if (jh < T.Np) {
-                                    uint32_t hq[4], lq[4];
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) tc::split2(y[2 * j], y[2 * j + 1], hq[j], lq[j]);
-                                    const int o = (rg0 + c) * xsbo + (jh >> 3) * 128 + (jh & 7) * 16;
-                                    *reinterpret_cast<uint4*>(xo_hi + o) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
-                                    *reinterpret_cast<uint4*>(xo_lo + o) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
-                                }
+                                *reinterpret_cast<float4*>(nz_s + r * (nj * 4) + 4 * jb) = make_float4(nz[0], nz[1], nz[2], nz[3]);
                             }
                         }
                     }
-                    tc::fence_before_sync();
-                    ptx::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&xr[mtg]);
-                    if (dbg && l < 4) dbg[3 + 2 * l] = clock64();
                 }
 
                 // ---------- heads -> Hd[j][row] --------------------------------------------------------
                 {
                     const uint32_t par0 = g_count & 1u;
                     ++g_count;
-                    if (mtg == 0 && quarter * 32 < T.NHp) {
+                    if (quarter * 32 < T.NHp) {
                         ptx::mbar_wait(&acc_full[0], par0);
                         tc::fence_after_sync();
                         if (dbg) dbg[10] = clock64();
-                        const uint32_t tcol = tmem_lane + (uint32_t)col0;
+                        const int jh = quarter * 32 + lane;
                         const float bj = jh < T.NHp ? bias[P.n_hidden * T.Np + jh] : 0.f;
+                        for (int c = cslice; c < nchunks; c += 4) {
+                            uint32_t v[8];
+                            tc::tmem_ld8(tmem_lane + c * 8, v);
+                            if (TERMS == 3) {
+                                uint32_t v1[8];
+                                tc::tmem_ld8(tmem_lane + N + c * 8, v1);
+                                tc::tmem_wait_ld();
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (c < nch) {
-                                uint32_t v[8];
-                                tc::tmem_ld8(tcol + c * 8, v);
-                                if (TERMS == 3) {
-                                    uint32_t v1[8], v2[8];
-                                    tc::tmem_ld8(tcol + N + c * 8, v1);
-                                    tc::tmem_ld8(tcol + 2 * N + c * 8, v2);
-                                    tc::tmem_wait_ld();
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j)
-                                        v[j] = __float_as_uint(__uint_as_float(v[j]) + (__uint_as_float(v1[j]) + __uint_as_float(v2[j])));
-                                } else {
-                                    tc::tmem_wait_ld();
-                                }
-                                if (jh < T.NHp) {
-                                    float4 a, b;
-                                    const float sc = 1.0f / (tc::kWScale * tc::kXScale);
-                                    a.x = fmaf(__uint_as_float(v[0]), sc, bj); a.y = fmaf(__uint_as_float(v[1]), sc, bj);
-                                    a.z = fmaf(__uint_as_float(v[2]), sc, bj); a.w = fmaf(__uint_as_float(v[3]), sc, bj);
-                                    b.x = fmaf(__uint_as_float(v[4]), sc, bj); b.y = fmaf(__uint_as_float(v[5]), sc, bj);
-                                    b.z = fmaf(__uint_as_float(v[6]), sc, bj); b.w = fmaf(__uint_as_float(v[7]), sc, bj);
-                                    float* dst = Hd + jh * N + col0 + c * 8;
-                                    *reinterpret_cast<float4*>(dst) = a;
-                                    *reinterpret_cast<float4*>(dst + 4) = b;
-                                }
+                                for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v1[j]));
+                            } else {
+                                tc::tmem_wait_ld();
+                            }
+                            if (jh < T.NHp) {
+                                float4 a, b;
+                                const float sc = 1.0f / (tc::kWScale * tc::kXScale);
+                                a.x = fmaf(__uint_as_float(v[0]), sc, bj); a.y = fmaf(__uint_as_float(v[1]), sc, bj);
+                                a.z = fmaf(__uint_as_float(v[2]), sc, bj); a.w = fmaf(__uint_as_float(v[3]), sc, bj);
+                                b.x = fmaf(__uint_as_float(v[4]), sc, bj); b.y = fmaf(__uint_as_float(v[5]), sc, bj);
+                                b.z = fmaf(__uint_as_float(v[6]), sc, bj); b.w = fmaf(__uint_as_float(v[7]), sc, bj);
+                                float* dst = Hd + jh * N + c * 8;
+                                *reinterpret_cast<float4*>(dst) = a;
+                                *reinterpret_cast<float4*>(dst + 4) = b;
                             }
                         }
                         tc::fence_before_sync();
@@ -740,45 +753,30 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 ptx::bar_sync(1, kSEpiThreads);
                 if (dbg) dbg[11] = clock64();
 
-                // ---------- final epilogue: sample, next state; work item = (row, block of 4 state dims) ----
-                for (int i = et; i < N * nj; i += kSEpiThreads) {
-                    const int jb = i / N, r = i - jb * N;
+                // ---------- final epilogue: sample, next state; work item = (row, state dim) ---------------
+                for (int i = et; i < N * D; i += kSEpiThreads) {
+                    const int d = i / N, r = i - d * N;
                     if (r >= nrows) continue;
-                    const int d0 = 4 * jb;
-                    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float mu = Hd[d * N + r];
+                    float lv = Hd[(D + d) * N + r];
+                    const float dmu = mu * v_dscale[d] + v_dmean[d];
+                    float delta = dmu;
                     if (!P.deterministic) {
-                        if (P.eps != nullptr) {
-                            const float* ep = P.eps + (P.row_mode == kRowsPlanner ? (size_t)t * eps_step_stride : 0) + (size_t)r_eps[r] * D;
-#pragma unroll
-                            for (int ii = 0; ii < 4; ++ii) nz[ii] = d0 + ii < D ? __ldg(ep + d0 + ii) : 0.f;
-                        } else {
-                            normal4_fast(P.seed, (uint32_t)jb, (uint32_t)r_rid[r], (uint32_t)t, (uint32_t)P.it, nz);
-                        }
+                        lv = fast_bounded_logvar(lv, v_maxlv[d], v_minlv[d]);
+                        delta = dmu + nz_s[r * (nj * 4) + d] * fast_exp((lv + v_2logstd[d]) * 0.5f);
                     }
-#pragma unroll
-                    for (int ii = 0; ii < 4; ++ii) {
-                        const int d = d0 + ii;
-                        if (d >= D) break;
-                        const float mu = Hd[d * N + r];
-                        float lv = Hd[(D + d) * N + r];
-                        const float dmu = mu * v_dscale[d] + v_dmean[d];
-                        float delta = dmu;
-                        if (!P.deterministic) {
-                            lv = fast_bounded_logvar(lv, v_maxlv[d], v_minlv[d]);
-                            delta = dmu + nz[ii] * fast_exp((lv + v_2logstd[d]) * 0.5f);
-                        }
-                        float* sp = S + r * (D + 1) + d;
-                        const float sn = env_postproc(P.env_id, *sp, delta, d);
-                        *sp = sn;
-                        if (P.row_mode == kRowsPlanner) {
-                            if (P.states != nullptr)
-                                P.states[(((size_t)t * P.m * P.n_local + r_src[r]) * P.p + r_pi[r]) * D + d] = sn;
-                        } else {
-                            const size_t o = (size_t)r_src[r] * D + d;
-                            if (P.next_obs) P.next_obs[o] = sn;
-                            if (P.mu_out) P.mu_out[o] = mu;
-                            if (P.lv_out) P.lv_out[o] = lv;
-                        }
+                    float* sp = S + r * (D + 3) + d;
+                    const float sn = env_postproc(P.env_id, *sp, delta, d);
+                    *sp = sn;
+                    if (P.env_id == CADM_ENV_HALFCHEETAH && d == 2) sincosf(sn, sp + (D + 1 - 2), sp + (D + 2 - 2));   // next step's features
+                    if (P.row_mode == kRowsPlanner) {
+                        if (P.states != nullptr)
+                            P.states[(((size_t)t * P.m * P.n_local + r_src[r]) * P.p + r_pi[r]) * D + d] = sn;
+                    } else {
+                        const size_t o = (size_t)r_src[r] * D + d;
+                        if (P.next_obs) P.next_obs[o] = sn;
+                        if (P.mu_out) P.mu_out[o] = mu;
+                        if (P.lv_out) P.lv_out[o] = lv;
                     }
                 }
                 tcs::cp_async_wait_all();                  // next step's actions have landed (issued at the top of the step)
@@ -786,7 +784,7 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 if (dbg) dbg[12] = clock64();
             }
             if (P.row_mode == kRowsPlanner && et < nrows) {
-                if (env_reward_reads_next(P.env_id)) ret += env_reward_next(P.env_id, S + et * (D + 1));
+                if (env_reward_reads_next(P.env_id)) ret += env_reward_next(P.env_id, S + et * (D + 3));
                 P.ret_p[(size_t)r_src[et] * P.p + r_pi[et]] = ret;
             }
         }
@@ -803,25 +801,14 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 static int g_tcs_smem = 0;
 
-// rows per tile: the smallest estimated launch time over N = 16 ... 64.  Per step a CTA spends about 3500 cycles in the
-// serial prologue / final epilogue and, per (K16 block, M tile) of its `pairs` weight blocks, two MMAs of
-// max(N, 32 + N / 2) + max(N / 2, 32 + N / 4) cycles (tools/tc_rate.py); the weight stream bounds it from below at
-// `stream_bytes` / min(64 B/clk per SM, 6000 B/clk over the active CTAs).
-int tcs_pick_rows(int rows_per_member, int E, int num_sms, long long stream_bytes, int pairs) {
-    int best = 16;
-    double best_cost = 1e30;
-    for (int N = 16; N <= kSMaxRows; N += 16) {
-        const int tiles = E * ((rows_per_member + N - 1) / N);
-        const int waves = (tiles + num_sms - 1) / num_sms;
-        const int active = tiles < num_sms ? tiles : num_sms;
-        const double bw = 6000.0 / active < 64.0 ? 6000.0 / active : 64.0;
-        const double m1 = N > 32 + N / 2 ? N : 32 + N / 2, m2 = N / 2 > 32 + N / 4 ? N / 2 : 32 + N / 4;
-        const double compute = 3500.0 + pairs * (m1 + m2);
-        const double stream = (double)stream_bytes / bw;
-        const double cost = waves * (compute > stream ? compute : stream);
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = N; }
-    }
-    return best;
+// rows per tile: the smallest multiple of 16 from 32 up whose tiles fit the SMs in one wave.  Below N = 128 an MMA costs
+// 32 + N / 4 cycles (tools/tc_rate.py: the 4 KB weight block is fetched from shared memory for every MMA), so a CTA's
+// time per step is nearly independent of N and the way to go faster is to use more SMs with fewer rows each; 16-row tiles
+// would need two waves for the BASELINE workloads and are only taken on request.
+int tcs_pick_rows(int rows_per_member, int E, int num_sms) {
+    int N = 32;
+    while (N < kSMaxRows && E * ((rows_per_member + N - 1) / N) > num_sms) N += 16;
+    return N;
 }
 
 cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long long wimg_member_stride, int terms, int kps,
@@ -842,8 +829,7 @@ cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long 
     const bool generic = (skew >> 28) & 1;     // diagnostic: force the table-driven MMA schedule
     T.nmt = T.Np > 128 ? 2 : 1;
     if (T.Np > 256 || T.NHp > 128 || kps < 1 || kps > kSMaxKps) return cudaErrorInvalidConfiguration;
-    const int pairs = T.nkb0 * T.nmt + (P.n_hidden - 1) * T.nkbH * T.nmt + T.nkbH;   // (K16 block, M tile) pairs per step
-    int N = rows_override > 0 ? rows_override : tcs_pick_rows(P.rows_per_member, P.E, num_sms, wimg_member_stride, pairs);
+    int N = rows_override > 0 ? rows_override : tcs_pick_rows(P.rows_per_member, P.E, num_sms);
     N = min(kSMaxRows, max(16, round_up(N, 16)));
     int tiles = (P.rows_per_member + N - 1) / N;
     N = min(N, round_up((P.rows_per_member + tiles - 1) / tiles, 16));      // balance the rows over the tiles
@@ -992,16 +978,15 @@ __global__ void __launch_bounds__(128, 1) tcs_gemm_selftest_kernel(const float* 
     for (int mt = 0; mt < nmt; ++mt) {
         const int j = mt * 128 + tid;
         for (int c = 0; c < rows; c += 8) {
-            uint32_t v[8], v1[8], v2[8];
+            uint32_t v[8], v1[8];
             tc::tmem_ld8(tl + mt * kSAccStride + c, v);
             tc::tmem_ld8(tl + mt * kSAccStride + rows + c, v1);
-            tc::tmem_ld8(tl + mt * kSAccStride + 2 * rows + c, v2);
             tc::tmem_wait_ld();
             if (j < Nout) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     float acc = __uint_as_float(v[q]);
-                    if (terms == 3) acc += __uint_as_float(v1[q]) + __uint_as_float(v2[q]);
+                    if (terms == 3) acc += __uint_as_float(v1[q]);
                     out[(size_t)(c + q) * Nout + j] = acc * (1.0f / (tc::kWScale * tc::kXScale));
                 }
             }

@@ -39,10 +39,13 @@ def run(variant, rows, kps, trace=False, skew=0):
             base = tr[t, 0]
             print(f"  step {t}: total {tr[t + 1, 0] - base} cycles")
             print("    epi :", " ".join(f"{n}={tr[t, i] - base}" for i, n in enumerate(names)))
+            print("    pro : reward_done=%d items_done=%d" % (tr[t, 13] - base, tr[t, 14] - base))
             print("    mma :", " ".join(f"g{g}:first_ready={tr[t, 32 + 4 * g] - base},issued={tr[t, 33 + 4 * g] - base}" for g in range(5)))
     model.engine.close()
 
 
-for rows in (32, 48, 64):
-    run(2, rows, 4, trace=(rows == 32))
-run(2, 32, 4, skew=1 << 28)
+run(2, 32, 4)
+run(2, 32, 4, skew=1 << 20)
+run(2, 32, 4, skew=2 << 20)
+run(2, 32, 4, skew=3 << 20)
+run(2, 32, 4, trace=True, skew=3 << 20)
