@@ -45,6 +45,9 @@ SIGNATURES = {
     "cadm_cem_rollout": (C.c_int, [_P, C.c_int32, C.c_uint64, _F, _F, _P]),
     "cadm_cem_returns_buffer": (C.c_void_p, [_P]),
     "cadm_cem_returns_slice_elems": (C.c_int64, [_P]),
+    "cadm_peer_export": (C.c_int, [_P, C.c_void_p]),
+    "cadm_peer_attach": (C.c_int, [_P, C.c_void_p, C.c_int32]),
+    "cadm_peer_enabled": (C.c_int, [_P]),
     "cadm_cem_refit": (C.c_int, [_P, C.c_int32, _P]),
     "cadm_cem_finish": (C.c_int, [_P, _F, _F, _F, _F, _P]),
     "cadm_plan_cem": (C.c_int, [_P, C.c_int32, _F, _F, _F, _F, _F, C.c_uint64, _F, _F, _F, _F, _F, _F, _P]),

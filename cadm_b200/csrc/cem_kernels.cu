@@ -75,6 +75,43 @@ cudaError_t launch_particle_mean(const float* ret_p, float* out, int count, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// mean over particles FUSED with the all-gather of the candidate returns (multi-GPU): the slice is written into every
+// rank's returns buffer through peer pointers (NVLink / NVSwitch stores), then flag `rank` of every rank is set to the
+// iteration's epoch with system-scope release ordering.  The refit kernel of each rank spins on its own flags.
+// ------------------------------------------------------------------------------------------------
+__global__ void particle_mean_scatter_kernel(const float* __restrict__ ret_p, int count, int p, unsigned char* const* peers,
+                                             int world, long long slice_off, long long flag_off, int epoch, int* block_counter) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        const float* r = ret_p + (size_t)i * p;
+        float s = 0.f;
+        for (int k = 0; k < p; ++k) s += r[k];           // the same fixed order as particle_mean_kernel: results do not depend on G
+        const float v = s / (float)p;
+        for (int g = 0; g < world; ++g) reinterpret_cast<float*>(peers[g] + slice_off)[i] = v;
+    }
+    __threadfence_system();                               // this block's stores are visible system-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(block_counter, 1);     // ... before it is counted
+        if (done == (int)gridDim.x - 1) {                 // last block: the whole slice has landed everywhere
+            *block_counter = 0;
+            __threadfence_system();
+            for (int g = 0; g < world; ++g) {
+                int* flag = reinterpret_cast<int*>(peers[g] + flag_off);
+                asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+            }
+        }
+    }
+}
+
+cudaError_t launch_particle_mean_scatter(const float* ret_p, int count, int p, unsigned char* const* peers, int world,
+                                         long long slice_off, long long flag_off, int epoch, int* block_counter, cudaStream_t stream) {
+    particle_mean_scatter_kernel<<<(count + 255) / 256, 256, 0, stream>>>(ret_p, count, p, peers, world, slice_off, flag_off, epoch,
+                                                                          block_counter);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // elite selection + refit (core/utils.py:171-182); one CTA per environment
 // ------------------------------------------------------------------------------------------------
 
@@ -109,6 +146,16 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
     const int K = R.k_elites;
     const int hA = R.h * R.A;
     float* el = reinterpret_cast<float*>(keys + R.npad);
+    if (R.peer_flags != nullptr) {
+        // fused all-gather: wait until every rank's slice of this iteration has landed in OUR returns buffer
+        if (tid < R.world) {
+            int seen;
+            do {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(R.peer_flags + tid) : "memory");
+            } while (seen - R.peer_epoch < 0);
+        }
+        __syncthreads();
+    }
     for (int i = tid; i < R.npad; i += blockDim.x) {
         unsigned long long key = ~0ull;
         if (i < n) {
@@ -161,10 +208,24 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
     for (int i = tid; i < K; i += blockDim.x)
         if (R.elites_log) R.elites_log[(size_t)mi * K + i] = s_el[i];
     if (R.stage_elites) {
-        // gather the elite sequences with independent, coalesced loads, then reduce from shared memory
-        for (int i = tid; i < K * hA; i += blockDim.x) {
-            const int jx = i / hA, k = i - jx * hA;
-            el[i] = elite_action(R, mi, s_el[jx], k, hA, R.mean[(size_t)mi * hA + k], R.var[(size_t)mi * hA + k]);
+        // gather the elite sequences with independent, coalesced loads (4 in flight per thread), then reduce from shared
+        // memory
+        const int total = K * hA;
+        for (int i0 = tid; i0 < total; i0 += 4 * blockDim.x) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total) {
+                    const int jx = i / hA, k = i - jx * hA;
+                    v[u] = elite_action(R, mi, s_el[jx], k, hA, R.mean[(size_t)mi * hA + k], R.var[(size_t)mi * hA + k]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total) el[i] = v[u];
+            }
         }
         __syncthreads();
     }
@@ -196,7 +257,7 @@ cudaError_t launch_refit(RefitParams R, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         g_refit_smem = (int)smem;
     }
-    const int threads = R.npad >= 1024 ? 1024 : max(R.npad, 256);
+    const int threads = 1024;      // the elite gather and the per-coordinate reductions want every thread the CTA can have
     refit_kernel<<<R.m, threads, smem, stream>>>(R);
     return cudaGetLastError();
 }

@@ -59,6 +59,14 @@ struct Engine {
     float* ret_p = nullptr;
     float* returns_buf = nullptr;
     float* returns_log = nullptr;
+    // exchange block (one allocation, exported over CUDA IPC): [2 parities][world, m_max, n_local] returns | [2][world] flags
+    unsigned char* xchg = nullptr;
+    size_t xchg_ret_bytes = 0, xchg_bytes = 0;
+    int* block_counter = nullptr;
+    unsigned char** peer_tab = nullptr;      // device array [world]: every rank's exchange block as seen from this device
+    std::vector<void*> peer_open;            // mappings to close
+    bool peers_on = false;
+    int epoch = 0;                           // exchange epoch: one per rollout since the peers were attached
     int* elites_log = nullptr;
     int* best = nullptr;
     // instrumentation
@@ -280,7 +288,12 @@ int cadm_plan_create(const CadmConfig* cfg, void** handle) {
     A(dalloc(E, &E->actions, mm * E->n_local * E->hA));
     A(dalloc(E, &E->actions_int, mm * E->n_local * c.horizon));
     A(dalloc(E, &E->ret_p, mm * E->n_local * c.particles));
-    A(dalloc(E, &E->returns_buf, mm * c.candidates));
+    E->xchg_ret_bytes = (mm * c.candidates * sizeof(float) + 255) / 256 * 256;
+    E->xchg_bytes = 2 * E->xchg_ret_bytes + 2 * 256 * ((c.world * sizeof(int) + 255) / 256);
+    A(dalloc(E, &E->xchg, E->xchg_bytes));
+    E->returns_buf = reinterpret_cast<float*>(E->xchg);          // parity 0 doubles as the buffer of the NCCL path
+    A(dalloc(E, &E->block_counter, 1));
+    A(dalloc(E, &E->peer_tab, (size_t)c.world));
     A(dalloc(E, &E->returns_log, (size_t)c.cem_iters * mm * c.candidates));
     A(dalloc(E, &E->elites_log, (size_t)c.cem_iters * mm * c.num_elites));
     A(dalloc(E, &E->best, mm));
@@ -299,6 +312,7 @@ int cadm_plan_destroy(void* handle) {
     Engine* E = H(handle);
     if (!E) return CADM_ERR_ARG;
     cudaDeviceSynchronize();
+    for (void* p : E->peer_open) cudaIpcCloseMemHandle(p);
     for (void* p : E->allocs) cudaFree(p);
     for (cudaEvent_t ev : E->ev) cudaEventDestroy(ev);
     delete E;
@@ -526,7 +540,19 @@ int cadm_cem_rollout(void* handle, int32_t it, uint64_t seed, const float* z, co
     if (int r = run_rollout(E, P, s)) return r;
 
     if (c.world > 1) {      // single rank: the refit kernel folds the particle mean in
-        CU(E, launch_particle_mean(E->ret_p, E->returns_buf + (size_t)c.rank * m * E->n_local, m * E->n_local, c.particles, s));
+        if (E->peers_on) {
+            // fused: particle mean + all-gather over peer memory; parity = epoch & 1 so that a rank one iteration ahead
+            // cannot overwrite a slice a slower rank is still reading
+            ++E->epoch;
+            const long long par = E->epoch & 1;
+            const long long slice_off = par * (long long)E->xchg_ret_bytes + (long long)c.rank * m * E->n_local * sizeof(float);
+            const long long flag_off = 2 * (long long)E->xchg_ret_bytes + par * 256 * (long long)((c.world * sizeof(int) + 255) / 256) +
+                                       (long long)c.rank * sizeof(int);
+            CU(E, launch_particle_mean_scatter(E->ret_p, m * E->n_local, c.particles, E->peer_tab, c.world, slice_off, flag_off, E->epoch,
+                                               E->block_counter, s));
+        } else {
+            CU(E, launch_particle_mean(E->ret_p, E->returns_buf + (size_t)c.rank * m * E->n_local, m * E->n_local, c.particles, s));
+        }
         E->launches++;
     }
     return CADM_OK;
@@ -548,6 +574,12 @@ static int refit_common(Engine* E, int it, uint64_t seed, const float* z, cudaSt
     R.npad = next_pow2(c.candidates);
     R.alpha = c.alpha; R.seed = seed;
     R.returns_buf = E->returns_buf; R.actions = E->actions;
+    if (c.world > 1 && E->peers_on) {
+        const long long par = E->epoch & 1;
+        R.returns_buf = reinterpret_cast<const float*>(E->xchg + par * E->xchg_ret_bytes);
+        R.peer_flags = reinterpret_cast<const int*>(E->xchg + 2 * E->xchg_ret_bytes + par * 256 * ((c.world * sizeof(int) + 255) / 256));
+        R.peer_epoch = E->epoch;
+    }
     R.z = z ? z + (size_t)it * m * c.candidates * E->hA : nullptr;
     R.mean = E->mean; R.var = E->var;
     R.returns_log = E->returns_log + (size_t)it * m * c.candidates;
@@ -695,6 +727,47 @@ int cadm_selftest_tc_gemm(const float* X, const float* W, int32_t K, int32_t N, 
     if (e != cudaSuccess) return fail(nullptr, CADM_ERR_CUDA, cudaGetErrorString(e));
     return CADM_OK;
 }
+
+int cadm_peer_export(void* handle, void* ipc_handle_out) {
+    Engine* E = H(handle);
+    if (!E || !ipc_handle_out) return CADM_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == CADM_IPC_HANDLE_BYTES, "CADM_IPC_HANDLE_BYTES must match cudaIpcMemHandle_t");
+    cudaIpcMemHandle_t h;
+    CU(E, cudaIpcGetMemHandle(&h, E->xchg));
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    return CADM_OK;
+}
+
+int cadm_peer_attach(void* handle, const void* ipc_handles, int32_t count) {
+    Engine* E = H(handle);
+    if (!E || !ipc_handles) return CADM_ERR_ARG;
+    const CadmConfig& c = E->cfg;
+    if (count != c.world) return fail(E, CADM_ERR_ARG, "expected one IPC handle per rank");
+    if (E->in_flight) return fail(E, CADM_ERR_STATE, "cannot attach peers in the middle of a decision");
+    std::vector<unsigned char*> tab(c.world, nullptr);
+    for (int r = 0; r < c.world; ++r) {
+        if (r == c.rank) { tab[r] = E->xchg; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const unsigned char*>(ipc_handles) + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (void* q : E->peer_open) cudaIpcCloseMemHandle(q);
+            E->peer_open.clear();
+            return fail(E, CADM_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        }
+        E->peer_open.push_back(p);
+        tab[r] = reinterpret_cast<unsigned char*>(p);
+    }
+    CU(E, cudaMemcpy(E->peer_tab, tab.data(), sizeof(unsigned char*) * c.world, cudaMemcpyHostToDevice));
+    CU(E, cudaMemset(E->xchg + 2 * E->xchg_ret_bytes, 0, E->xchg_bytes - 2 * E->xchg_ret_bytes));      // flags: epoch 0
+    CU(E, cudaDeviceSynchronize());
+    E->epoch = 0;
+    E->peers_on = true;
+    return CADM_OK;
+}
+
+int cadm_peer_enabled(void* handle) { return handle && H(handle)->peers_on ? 1 : 0; }
 
 int cadm_set_option(void* handle, const char* name, int32_t value) {
     Engine* E = H(handle);

@@ -33,6 +33,8 @@ struct RefitParams {
     const float* ret_p;             // nullable: [m, n_global, p] particle returns (world == 1: particle mean folded in)
     int p;
     int stage_elites;               // set by the launcher: elite rows fit in shared memory
+    const int* peer_flags;          // nullable: [world] arrival epochs written by the peers (fused peer-memory all-gather)
+    int peer_epoch;                 // wait until every peer_flags[r] >= peer_epoch before reading returns_buf
     // random shooting (mode_rs): argmax only
     int mode_rs;
     int* best;                      // [m]
@@ -53,6 +55,11 @@ struct EncoderParams {
 
 cudaError_t launch_sample_actions(const SampleParams& S, cudaStream_t stream);
 cudaError_t launch_particle_mean(const float* ret_p, float* out, int count, int p, cudaStream_t stream);
+// particle mean + all-gather in one kernel: every rank writes its [count] slice straight into the returns buffer of EVERY
+// rank (peer memory over NVLink) and then publishes `epoch` in flag `rank` of every rank.
+//   peers[r] = base of rank r's exchange block; slice_off / flag_off = byte offsets of this rank's slice / flag in a block
+cudaError_t launch_particle_mean_scatter(const float* ret_p, int count, int p, unsigned char* const* peers, int world,
+                                         long long slice_off, long long flag_off, int epoch, int* block_counter, cudaStream_t stream);
 cudaError_t launch_refit(RefitParams R, cudaStream_t stream);
 cudaError_t launch_rs_gather(const float* actions, const int* actions_int, const int* best, int m, int n_local, int h,
                              int A, float* action, int* action_int, cudaStream_t stream);

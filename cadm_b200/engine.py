@@ -274,6 +274,23 @@ class PlannerEngine:
         ptr = self.lib.cadm_cem_returns_buffer(self._h)
         return torch.as_tensor(_CudaView(ptr, (self.cfg.world, self._m, self.n_local)), device=self.device)
 
+    def peer_export(self) -> bytes:
+        """CUDA IPC handle of this rank's exchange block (cadm_peer_export)."""
+        buf = C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            self._chk(self.lib.cadm_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_attach(self, handles: Sequence[bytes]):
+        """Attach every rank's exchange block (rank order); afterwards the all-gather is fused into the rollout phase."""
+        blob = b"".join(handles)
+        with torch.cuda.device(self.device):
+            self._chk(self.lib.cadm_peer_attach(self._h, blob, len(handles)))
+
+    @property
+    def peers_enabled(self) -> bool:
+        return bool(self.lib.cadm_peer_enabled(self._h))
+
     def cem_refit(self, it):
         with torch.cuda.device(self.device):
             self._chk(self.lib.cadm_cem_refit(self._h, it, self._stream()))

@@ -149,6 +149,19 @@ int cadm_cem_rollout(void* handle, int32_t it, uint64_t seed, const float* z, co
 float* cadm_cem_returns_buffer(void* handle);
 int64_t cadm_cem_returns_slice_elems(void* handle);   /* m * n_local of the decision in flight */
 
+/* ---- fused all-gather over peer memory (optional; replaces the host-side ncclAllGather above) ----
+ * Every rank exports its exchange block (returns buffer + arrival flags, one CUDA allocation) as a CUDA IPC handle,
+ * the host exchanges the `world` handles (any transport; cadm_b200/parallel.py uses torch.distributed), and each rank
+ * attaches them.  From then on cadm_cem_rollout averages over the particles AND stores the rank's slice into every
+ * rank's returns buffer over NVLink in the same kernel, and cadm_cem_refit waits on the arrival flags on the device:
+ * no collective call and no host synchronisation between the phases.  All ranks must be on one node and must call the
+ * phases in lockstep (they do: the plan is data-independent).  The caller makes sure every rank has attached before
+ * any rank starts a decision (a barrier after cadm_peer_attach). */
+#define CADM_IPC_HANDLE_BYTES 64
+int cadm_peer_export(void* handle, void* ipc_handle_out /* CADM_IPC_HANDLE_BYTES */);
+int cadm_peer_attach(void* handle, const void* ipc_handles /* world x CADM_IPC_HANDLE_BYTES, rank order */, int32_t count);
+int cadm_peer_enabled(void* handle);
+
 /* top_k + gather + refit + EMA (core/utils.py:171-182) from the gathered returns buffer. */
 int cadm_cem_refit(void* handle, int32_t it, void* stream);
 
