@@ -262,6 +262,24 @@ def run_engine(args, rank, world, local_rank):
         d2h = 4 * m * h * env.act_dim
         e2e = {"value": units * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * e2e_s / args.steps}
+        # the same control step with the sampler-side state on the device (PlannerSession): only the observation goes up and
+        # the first action comes down; warm start, init_var and the history buffers stay in HBM
+        from cadm_b200.samplers import PlannerSession
+        sess = PlannerSession(model, m, state_diff=True)
+        obs64 = inp["obs"].astype(np.float64)
+        for i in range(2):
+            a = sess.act(obs64)
+            sess.observe(obs64 + 0.01, None)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            a = sess.act(obs64)
+            sess.observe(obs64 + 0.01 * (i + 1), None)
+        torch.cuda.synchronize()
+        sess_s = time.perf_counter() - t0
+        e2e["session"] = {"value": units * args.steps / sess_s, "unit": UNIT, "ms_per_step": 1e3 * sess_s / args.steps,
+                          "h2d_bytes_per_step": 4 * m * env.obs_dim * 2, "d2h_bytes_per_step": 4 * m * env.act_dim,
+                          "what": "PlannerSession.act + observe: warm start / init_var / history buffers resident on the device"}
     else:
         # multi-rank: same decision through the sharded planner fed from pinned host tensors
         pin = {k: torch.from_numpy(v).pin_memory() for k, v in inp.items()}

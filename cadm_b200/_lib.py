@@ -52,6 +52,10 @@ SIGNATURES = {
     "cadm_cem_finish": (C.c_int, [_P, _F, _F, _F, _F, _P]),
     "cadm_plan_cem": (C.c_int, [_P, C.c_int32, _F, _F, _F, _F, _F, C.c_uint64, _F, _F, _F, _F, _F, _F, _P]),
     "cadm_plan_cem_host": (C.c_int, [_P, C.c_int32, _F, _F, _F, _F, _F, C.c_uint64, _F, _P]),
+    "cadm_session_reset": (C.c_int, [_P, C.c_int32, C.c_void_p, _P]),
+    "cadm_session_act": (C.c_int, [_P, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, _P]),
+    "cadm_session_observe": (C.c_int, [_P, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, _P]),
+    "cadm_session_state": (C.c_int, [_P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _P]),
     "cadm_plan_rs": (C.c_int, [_P, C.c_int32, _F, _F, _F, C.c_uint64, _F, _F, _F, _F, _F, _F, _F, _P]),
     "cadm_set_precision": (C.c_int, [_P, C.c_int32]),
     "cadm_selftest_tc_gemm": (C.c_int, [_F, _F, C.c_int32, C.c_int32, C.c_int32, _F, _P]),

@@ -325,6 +325,94 @@ cudaError_t launch_encoder(const EncoderParams& Q, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// sampler-side state on the device: what cadm/samplers/sampler.py keeps in NumPy between two
+// get_actions() calls -- the warm-start plan prev_sol, the K-step history buffers and their fill counters
+// ------------------------------------------------------------------------------------------------
+// after a decision (sampler.py:118-120): actions = clip(plan)[:, 0]; prev_sol[:, :-1] = clip(plan)[:, 1:]; prev_sol[:, -1] = 0
+// (the clip is get_action's np.clip, mlp_ensemble_cem_dynamics.py:205-206)
+__global__ void session_shift_kernel(const float* __restrict__ mean, float* __restrict__ prev_sol, float* __restrict__ action, int h, int A) {
+    const int mi = blockIdx.x, hA = h * A;
+    for (int k = threadIdx.x; k < hA; k += blockDim.x) {
+        const float v = fminf(fmaxf(mean[(size_t)mi * hA + k], -1.0f), 1.0f);
+        if (k < A) action[(size_t)mi * A + k] = v;
+        else prev_sol[(size_t)mi * hA + k - A] = v;
+    }
+    __syncthreads();        // every read of row mi precedes the zeroing of its tail (mean and prev_sol may alias)
+    for (int k = threadIdx.x; k < A; k += blockDim.x) prev_sol[(size_t)mi * hA + hA - A + k] = 0.f;
+}
+
+cudaError_t launch_session_shift(const float* mean, float* prev_sol, float* action, int m, int h, int A, cudaStream_t stream) {
+    session_shift_kernel<<<m, 256, 0, stream>>>(mean, prev_sol, action, h, A);
+    return cudaGetLastError();
+}
+
+// after the environment step (sampler.py:164-195): append (next_obs - obs | obs, action) to the history -- left to right
+// while it fills, sliding afterwards -- then, for finished episodes, clear the history, the counter and the warm start
+__global__ void session_observe_kernel(const float* __restrict__ obs, const float* __restrict__ next_obs, const float* __restrict__ action,
+                                       const unsigned char* __restrict__ done, float* hist_obs, float* hist_act, int* counts,
+                                       float* prev_sol, int D, int A, int K, int hA, int state_diff) {
+    const int mi = blockIdx.x, tid = threadIdx.x;
+    float* ho = hist_obs + (size_t)mi * D * K;
+    float* ha = hist_act + (size_t)mi * A * K;
+    const int cnt = counts[mi];
+    const bool fin = done != nullptr && done[mi] != 0;
+    if (!fin) {
+        if (cnt >= K) {
+            // slide by one entry; each thread moves its own elements from the back of a register copy
+            for (int base = 0; base < D * (K - 1); base += blockDim.x) {
+                const int i = base + tid;
+                const float v = i < D * (K - 1) ? ho[i + D] : 0.f;
+                __syncthreads();
+                if (i < D * (K - 1)) ho[i] = v;
+                __syncthreads();
+            }
+            for (int base = 0; base < A * (K - 1); base += blockDim.x) {
+                const int i = base + tid;
+                const float v = i < A * (K - 1) ? ha[i + A] : 0.f;
+                __syncthreads();
+                if (i < A * (K - 1)) ha[i] = v;
+                __syncthreads();
+            }
+        }
+        const int slot = cnt < K ? cnt : K - 1;
+        for (int d = tid; d < D; d += blockDim.x) {
+            const float o = obs[(size_t)mi * D + d];
+            ho[slot * D + d] = state_diff ? next_obs[(size_t)mi * D + d] - o : o;
+        }
+        for (int a = tid; a < A; a += blockDim.x) ha[slot * A + a] = action[(size_t)mi * A + a];
+        if (tid == 0) counts[mi] = cnt + 1;
+    } else {
+        for (int i = tid; i < D * K; i += blockDim.x) ho[i] = 0.f;
+        for (int i = tid; i < A * K; i += blockDim.x) ha[i] = 0.f;
+        for (int i = tid; i < hA; i += blockDim.x) prev_sol[(size_t)mi * hA + i] = 0.f;
+        if (tid == 0) counts[mi] = 0;
+    }
+}
+
+cudaError_t launch_session_observe(const float* obs, const float* next_obs, const float* action, const unsigned char* done,
+                                   float* hist_obs, float* hist_act, int* counts, float* prev_sol, int m, int D, int A, int K, int hA,
+                                   int state_diff, cudaStream_t stream) {
+    session_observe_kernel<<<m, 256, 0, stream>>>(obs, next_obs, action, done, hist_obs, hist_act, counts, prev_sol, D, A, K, hA, state_diff);
+    return cudaGetLastError();
+}
+
+__global__ void session_reset_kernel(const unsigned char* __restrict__ mask, float* hist_obs, float* hist_act, int* counts,
+                                     float* prev_sol, int DK, int AK, int hA) {
+    const int mi = blockIdx.x, tid = threadIdx.x;
+    if (mask != nullptr && mask[mi] == 0) return;
+    for (int i = tid; i < DK; i += blockDim.x) hist_obs[(size_t)mi * DK + i] = 0.f;
+    for (int i = tid; i < AK; i += blockDim.x) hist_act[(size_t)mi * AK + i] = 0.f;
+    for (int i = tid; i < hA; i += blockDim.x) prev_sol[(size_t)mi * hA + i] = 0.f;
+    if (tid == 0) counts[mi] = 0;
+}
+
+cudaError_t launch_session_reset(const unsigned char* mask, float* hist_obs, float* hist_act, int* counts, float* prev_sol, int m,
+                                 int DK, int AK, int hA, cudaStream_t stream) {
+    session_reset_kernel<<<m, 256, 0, stream>>>(mask, hist_obs, hist_act, counts, prev_sol, DK, AK, hA);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight packing for the fp32 path: [E, in, out] -> zero-padded k-major image
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_f32_kernel(float* dst, const float* src, int E, int in, int out, int Kp, int Np, int col0,

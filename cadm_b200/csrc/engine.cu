@@ -69,6 +69,11 @@ struct Engine {
     int epoch = 0;                           // exchange epoch: one per rollout since the peers were attached
     int* elites_log = nullptr;
     int* best = nullptr;
+    // sampler-side state kept on the device (cadm_session_*)
+    float *s_prev = nullptr, *s_var = nullptr, *s_obs = nullptr, *s_next = nullptr, *s_act = nullptr, *s_hobs = nullptr, *s_hact = nullptr;
+    int* s_counts = nullptr;
+    unsigned char* s_mask = nullptr;
+    bool s_var_set = false;
     // instrumentation
     long long launches = 0;
     const char* kernel_name = "rollout_f32_kernel";
@@ -297,6 +302,10 @@ int cadm_plan_create(const CadmConfig* cfg, void** handle) {
     A(dalloc(E, &E->returns_log, (size_t)c.cem_iters * mm * c.candidates));
     A(dalloc(E, &E->elites_log, (size_t)c.cem_iters * mm * c.num_elites));
     A(dalloc(E, &E->best, mm));
+    A(dalloc(E, &E->s_prev, mm * E->hA)); A(dalloc(E, &E->s_var, mm * E->hA));
+    A(dalloc(E, &E->s_obs, mm * c.obs_dim)); A(dalloc(E, &E->s_next, mm * c.obs_dim)); A(dalloc(E, &E->s_act, mm * c.act_dim));
+    A(dalloc(E, &E->s_hobs, mm * c.obs_dim * K)); A(dalloc(E, &E->s_hact, mm * c.act_dim * K));
+    A(dalloc(E, &E->s_counts, mm)); A(dalloc(E, &E->s_mask, mm));
     A(dalloc(E, &E->dbg, 64 * 64));
     if (e != cudaSuccess) {
         std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(e);
@@ -658,6 +667,80 @@ int cadm_plan_cem_host(void* handle, int32_t m, const float* obs_host, const flo
     CU(E, cudaMemcpyAsync(action_host, E->mean, n * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU(E, cudaStreamSynchronize(s));
     for (size_t i = 0; i < n; ++i) action_host[i] = fminf(fmaxf(action_host[i], -1.0f), 1.0f);   // get_action clip
+    return CADM_OK;
+}
+
+// ---- sampler-side state on the device ----------------------------------------------------------
+int cadm_session_reset(void* handle, int32_t m, const uint8_t* mask_host, void* stream) {
+    Engine* E = H(handle);
+    if (!E) return CADM_ERR_ARG;
+    const CadmConfig& c = E->cfg;
+    if (m < 1 || m > c.m_max) return fail(E, CADM_ERR_ARG, "m out of range (1..m_max)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int K = c.ctx_dim > 0 ? c.hist_len : 1;
+    if (mask_host) CU(E, cudaMemcpyAsync(E->s_mask, mask_host, m, cudaMemcpyHostToDevice, s));
+    CU(E, launch_session_reset(mask_host ? E->s_mask : nullptr, E->s_hobs, E->s_hact, E->s_counts, E->s_prev, m, c.obs_dim * K,
+                               c.act_dim * K, E->hA, s));
+    E->launches++;
+    if (!E->s_var_set) {        // init_var = 2^2 / 16 for every coordinate, never updated (sampler.py:53, quirk Q7)
+        std::vector<float> v((size_t)c.m_max * E->hA, 0.25f);
+        CU(E, cudaMemcpyAsync(E->s_var, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+        CU(E, cudaStreamSynchronize(s));
+        E->s_var_set = true;
+    }
+    return CADM_OK;
+}
+
+int cadm_session_act(void* handle, int32_t m, const float* obs_host, uint64_t seed, float* action_host, void* stream) {
+    Engine* E = H(handle);
+    if (!E) return CADM_ERR_ARG;
+    const CadmConfig& c = E->cfg;
+    if (c.world != 1) return fail(E, CADM_ERR_STATE, "sessions are single-rank");
+    if (c.discrete) return fail(E, CADM_ERR_UNSUPPORTED, "sessions plan with CEM (continuous actions)");
+    if (m < 1 || m > c.m_max || !obs_host || !action_host) return fail(E, CADM_ERR_ARG, "bad arguments");
+    if (!E->s_var_set) return fail(E, CADM_ERR_STATE, "cadm_session_reset has not been called");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(E, cudaMemcpyAsync(E->s_obs, obs_host, (size_t)m * c.obs_dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    // plan from the warm start with the constant variance; the history buffers feed the context encoder
+    if (int r = cadm_plan_cem(handle, m, E->s_obs, E->s_hobs, E->s_hact, E->s_prev, E->s_var, seed, nullptr, nullptr, nullptr, nullptr,
+                              nullptr, nullptr, stream))
+        return r;
+    CU(E, launch_session_shift(E->mean, E->s_prev, E->s_act, m, c.horizon, c.act_dim, s));
+    E->launches++;
+    CU(E, cudaMemcpyAsync(action_host, E->s_act, (size_t)m * c.act_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(E, cudaStreamSynchronize(s));
+    return CADM_OK;
+}
+
+int cadm_session_observe(void* handle, int32_t m, const float* next_obs_host, const uint8_t* done_host, int32_t state_diff,
+                         void* stream) {
+    Engine* E = H(handle);
+    if (!E) return CADM_ERR_ARG;
+    const CadmConfig& c = E->cfg;
+    if (m < 1 || m > c.m_max || !next_obs_host) return fail(E, CADM_ERR_ARG, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int K = c.ctx_dim > 0 ? c.hist_len : 1;
+    CU(E, cudaMemcpyAsync(E->s_next, next_obs_host, (size_t)m * c.obs_dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (done_host) CU(E, cudaMemcpyAsync(E->s_mask, done_host, m, cudaMemcpyHostToDevice, s));
+    CU(E, launch_session_observe(E->s_obs, E->s_next, E->s_act, done_host ? E->s_mask : nullptr, E->s_hobs, E->s_hact, E->s_counts,
+                                 E->s_prev, m, c.obs_dim, c.act_dim, K, E->hA, state_diff, s));
+    E->launches++;
+    return CADM_OK;
+}
+
+int cadm_session_state(void* handle, int32_t m, float* prev_sol_host, float* hist_obs_host, float* hist_act_host,
+                       int32_t* counts_host, void* stream) {
+    Engine* E = H(handle);
+    if (!E) return CADM_ERR_ARG;
+    const CadmConfig& c = E->cfg;
+    if (m < 1 || m > c.m_max) return fail(E, CADM_ERR_ARG, "m out of range (1..m_max)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int K = c.ctx_dim > 0 ? c.hist_len : 1;
+    if (prev_sol_host) CU(E, cudaMemcpyAsync(prev_sol_host, E->s_prev, (size_t)m * E->hA * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (hist_obs_host) CU(E, cudaMemcpyAsync(hist_obs_host, E->s_hobs, (size_t)m * c.obs_dim * K * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (hist_act_host) CU(E, cudaMemcpyAsync(hist_act_host, E->s_hact, (size_t)m * c.act_dim * K * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (counts_host) CU(E, cudaMemcpyAsync(counts_host, E->s_counts, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(E, cudaStreamSynchronize(s));
     return CADM_OK;
 }
 

@@ -64,6 +64,13 @@ cudaError_t launch_refit(RefitParams R, cudaStream_t stream);
 cudaError_t launch_rs_gather(const float* actions, const int* actions_int, const int* best, int m, int n_local, int h,
                              int A, float* action, int* action_int, cudaStream_t stream);
 cudaError_t launch_encoder(const EncoderParams& Q, cudaStream_t stream);
+// sampler-side state kept on the device (cadm/samplers/sampler.py:49-57,107-120,164-195)
+cudaError_t launch_session_shift(const float* mean, float* prev_sol, float* action, int m, int h, int A, cudaStream_t stream);
+cudaError_t launch_session_observe(const float* obs, const float* next_obs, const float* action, const unsigned char* done,
+                                   float* hist_obs, float* hist_act, int* counts, float* prev_sol, int m, int D, int A, int K, int hA,
+                                   int state_diff, cudaStream_t stream);
+cudaError_t launch_session_reset(const unsigned char* mask, float* hist_obs, float* hist_act, int* counts, float* prev_sol, int m,
+                                 int DK, int AK, int hA, cudaStream_t stream);
 cudaError_t launch_pack_f32(float* dst, const float* src, int E, int in, int out, int Kp, int Np, int col0,
                             long long member_stride, long long layer_off, int clear, cudaStream_t stream);
 cudaError_t launch_pack_bias(float* dst, const float* src, int E, int out, int col0, long long bias_stride, long long off,

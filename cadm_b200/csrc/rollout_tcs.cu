@@ -615,14 +615,16 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 {
                     const int par_off = (t & 1) * N * A * 4;
                     const bool onehot_mode = P.discrete && P.row_mode == kRowsPlanner;
-                    for (int i = et; i < K0 * (N >> 3); i += kSEpiThreads) {
-                        const int rg = i / K0, k = i - rg * K0;
+                    // one work item = (feature k, pair of rows): 512 items for 32 features x 32 rows, one short chain per thread
+                    // (8 rows per thread was a ~900-cycle dependent chain on 128 threads); 4-byte stores into the MN-major layout
+                    for (int i = et; i < K0 * (N >> 1); i += kSEpiThreads) {
+                        const int rp = i / K0, k = i - rp * K0;
                         const int4 fi = feat_i[k];
                         const float2 ff = feat_f[k];
-                        float y[8];
+                        float y[2];
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            const int r = rg * 8 + jj;
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const int r = rp * 2 + jj;
                             float src = *reinterpret_cast<const float*>(smem + fi.x + r * fi.y + ((fi.z & 1) ? par_off : 0));
                             if (onehot_mode && (fi.z & 1)) {
                                 const int oh = r < nrows ? __ldg(P.actions_int + (size_t)r_src[r] * P.h + t) : -1;
@@ -630,7 +632,11 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                             }
                             y[jj] = r < nrows ? (src - ff.x) * ff.y : 0.f;
                         }
-                        tcs::store_rows8(x0hi, x0hi + L.xbytes, xsbo, rg, k, y);
+                        uint32_t hq, lq;
+                        tc::split2(y[0], y[1], hq, lq);
+                        const int o = (rp >> 2) * xsbo + (k >> 3) * 128 + (k & 7) * 16 + (rp & 3) * 4;
+                        *reinterpret_cast<uint32_t*>(x0hi + o) = hq;
+                        *reinterpret_cast<uint32_t*>(x0hi + L.xbytes + o) = lq;
                     }
                     if (dbg) dbg[14] = clock64();
                     ptx::fence_proxy_async();

@@ -182,6 +182,21 @@ int cadm_plan_cem_host(void* handle, int32_t m, const float* obs_host, const flo
                        const float* cp_act_host, const float* init_mean_host, const float* init_var_host,
                        uint64_t seed, float* action_host, void* stream);
 
+/* ---- sampler-side state on the device (the step either side of the decision) ----
+ * What cadm/samplers/sampler.py keeps in NumPy between two get_actions() calls lives in the engine instead: the warm-start
+ * plan `prev_sol` (sampler.py:52,118-119), the constant `init_var` = 0.25 (:53), the K-step history buffers that feed the
+ * context encoder and their fill counters (:94-97,164-178), and the per-episode resets (:55-57,190-195).  A control step
+ * is then  cadm_session_act (H2D of obs [m, D], one decision, D2H of the clipped first actions [m, A])  followed, after
+ * the environment step, by  cadm_session_observe (H2D of next_obs [m, D] and done [m]; asynchronous).  world == 1. */
+int cadm_session_reset(void* handle, int32_t m, const uint8_t* mask_host /* [m] or NULL = all */, void* stream);
+int cadm_session_act(void* handle, int32_t m, const float* obs_host, uint64_t seed, float* action_host, void* stream);
+/* history entry = next_obs - obs when state_diff != 0 (run_cadm_pets.py:137 default), else obs (sampler.py:166-177) */
+int cadm_session_observe(void* handle, int32_t m, const float* next_obs_host, const uint8_t* done_host, int32_t state_diff,
+                         void* stream);
+/* copies of the state for inspection (any pointer may be NULL): prev_sol [m, h, A], history [m, D*K] / [m, A*K], counts [m] */
+int cadm_session_state(void* handle, int32_t m, float* prev_sol_host, float* hist_obs_host, float* hist_act_host,
+                       int32_t* counts_host, void* stream);
+
 /* Random shooting, `_get_rs_action` (core/utils.py:186-246 / 490-561).  u: explicit draws, [m, n_local, h, A]
  * uniform(-1,1) actions (continuous) or NULL (Philox); for discrete models u_int [m, n_local, h] int32 or NULL.
  * world == 1 only.  -> action [m, A] (continuous, unclipped) or action_int [m], returns [m, n], best [m]. */

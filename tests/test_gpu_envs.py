@@ -136,3 +136,70 @@ def test_checkpoint_roundtrip_reference_format(tmp_path):
     assert list(b.normalization.keys()) == list(a.normalization.keys())
     with pytest.raises(NotImplementedError):
         b.fit(None, None, None)
+
+
+@pytest.mark.parametrize("config", ["C3", "C2"])
+def test_session_matches_host_loop(config):
+    """Sampler-side state on the device (cadm_session_*): warm-start shift, constant init_var, K-step history buffers
+    filling left to right and then sliding, per-episode resets -- against the NumPy loop of cadm/samplers/sampler.py:107-195
+    driving get_actions() with host arrays.  Same engine arithmetic, same seeds: the actions must agree bit for bit."""
+    from cadm_b200.policies.mpc_controller import MPCController
+    from cadm_b200.samplers import PlannerSession
+    from cadm_b200.synth import build_model
+    m, horizon = 3, 30
+    ctx = config == "C3"
+    host_model, env, cfg = build_model(config, m_max=m, seed=1, candidates=64)
+    dev_model, _, _ = build_model(config, m_max=m, seed=1, candidates=64)
+    policy = MPCController(name="policy", env=env, dynamics_model=host_model, use_cem=True, n_candidates=64, horizon=horizon,
+                           num_rollouts=m, context=ctx)
+    A, D = env.act_dim, env.obs_dim
+    K = 10 if ctx else 1
+    session = PlannerSession(dev_model, m, state_diff=True)
+    prev_sol = np.tile(0., [m, horizon, A])
+    init_var = np.tile(np.square(2) / 16, [m, horizon, A])
+    history_state = np.zeros((m, D * K))
+    history_act = np.zeros((m, A * K))
+    counts = [0] * m
+    rng = np.random.default_rng(0)
+    obses = (0.1 * rng.standard_normal((m, D))).astype(np.float32).astype(np.float64)     # fp32-representable, like env output
+    for step in range(K + 4):
+        if ctx:
+            sols, _ = policy.get_actions(obses, init_mean=prev_sol, init_var=init_var, cp_obs=history_state, cp_act=history_act)
+        else:
+            sols, _ = policy.get_actions(obses, init_mean=prev_sol, init_var=init_var)
+        prev_sol[:, :-1] = sols[:, 1:].copy()
+        prev_sol[:, -1:] = 0.
+        actions = sols[:, 0].copy()
+        got = session.act(obses)
+        assert np.array_equal(got, actions), step
+        next_obses = (obses + 0.01 * rng.standard_normal((m, D))).astype(np.float32).astype(np.float64)   # stub env step
+        dones = np.zeros(m, bool)
+        if step == K + 1:
+            dones[1] = True                                   # one episode ends after the buffers have started sliding
+        for idx in range(m):                                  # sampler.py:164-195
+            if counts[idx] < K:
+                history_state[idx][counts[idx] * D:(counts[idx] + 1) * D] = next_obses[idx] - obses[idx]
+                history_act[idx][counts[idx] * A:(counts[idx] + 1) * A] = actions[idx]
+            else:
+                history_state[idx][:-D] = history_state[idx][D:]
+                history_state[idx][-D:] = next_obses[idx] - obses[idx]
+                history_act[idx][:-A] = history_act[idx][A:]
+                history_act[idx][-A:] = actions[idx]
+            if dones[idx]:
+                prev_sol[idx] = 0.
+                counts[idx] = 0
+                history_state[idx] = 0.
+                history_act[idx] = 0.
+            else:
+                counts[idx] += 1
+        session.observe(next_obses, dones)
+        p, ho, ha, cnt = session.state()
+        assert np.array_equal(p, prev_sol.astype(np.float32)), step
+        if ctx:
+            assert np.array_equal(ho, history_state.astype(np.float32)), step
+            assert np.array_equal(ha, history_act.astype(np.float32)), step
+            assert list(cnt) == counts
+        obses = next_obses
+    session.reset(idx=[0])
+    p, ho, ha, cnt = session.state()
+    assert not p[0].any() and not ho[0].any() and cnt[0] == 0 and p[2].any()
