@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
     uint64_t* x_ready = w_empty + 8;
     uint64_t* acc_full = x_ready + kMaxKB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    volatile uint32_t* done = tmem_slot + 1;       // [2]: producer / MMA thread finished (the other lanes of their warps sleep on it)
 
     float* v_obs_mean = vec;
     float* v_obs_den = vec + kMaxObs;
@@ -233,6 +234,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
         for (int k = 0; k < kMaxKB; ++k) ptx::mbar_init(&x_ready[k], 4);
         ptx::mbar_init(&acc_full[0], 1);
         ptx::mbar_init(&acc_full[1], 1);
+        done[0] = 0u;
+        done[1] = 0u;
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -270,67 +273,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                     }
                 }
             }
+            done[0] = 1u;
+        } else {
+            // lanes parked at a barrier keep competing for issue slots with the working lane of their own warp (measured in
+            // rollout_tcs.cu); sleeping lanes do not
+            while (!done[0]) __nanosleep(2000);
         }
+        __syncwarp();
     }
     // ======================= warp 1: MMA issuer ==================================================
-    // The whole warp walks the schedule with warp-uniform state (so descriptors live in uniform registers); one elected
-    // lane issues the tcgen05 instructions.  (Issuing from inside `if (lane == 0)` makes ptxas wrap every UTCHMMA in an
-    // ELECT + 7 x R2UR waterfall loop: ~160 cycles per MMA, slower than the tensor pipe itself.)
+    // ONE elected thread walks the whole schedule inside a single elect.sync region: ptxas keeps the descriptors in uniform
+    // registers and issues the three UTCHMMAs of a K block back to back.  (Electing per K block from a warp-uniform walk
+    // cost ~2x the MMA time in instruction latency -- a lone thread has no latency hiding, so its loop has to be lean; see
+    // rollout_tcs.cu for the measurements.)  The tcgen05 fence is needed once per GEMM (accumulator hand-over), not per block.
     else if (warp == 1) {
-        Ring rc{0, 0, nstage};
-        uint32_t xphase = 0;          // bit kb = parity to wait for on x_ready[kb]
-        uint32_t g_count = 0;         // running GEMM index: accumulator buffer = g & 1
-        const uint32_t xhi_a = ptx::smem_u32(xhi), xlo_a = ptx::smem_u32(xlo), w_a = ptx::smem_u32(wring);
-        const uint32_t desc_hi_const = (1u << 14) | 8u;             // version 1 (bit 46), SBO = 128 B  (upper 32 bits)
-        for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
-            for (int t = 0; t < P.h; ++t) {
-                for (int g = 0; g < gemms_per_step; ++g) {
-                    const int nkb = g == 0 ? T.nkb0 : T.nkbH;
-                    const uint32_t N = g == P.n_hidden ? (uint32_t)T.NHp : (uint32_t)T.Np;
-                    const uint32_t d_tmem = tmem_base + (g_count & 1u) * 256u;
-                    const uint32_t idesc = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
-                    const uint32_t b_lbo = (N >> 0) << 16;          // LBO = 16 N bytes -> (16 N) >> 4 = N, at bits [16, 30)
-                    long long* dbg = (T.dbg && blockIdx.x == 0 && lane == 0 && tile == (int)blockIdx.x && t < 64 && g < 5)
-                                         ? T.dbg + t * 64 + 32 + 4 * g : nullptr;
-                    long long xw = 0, ww = 0, iw = 0;
-                    for (int pos = 0; pos < nkb; ++pos) {
-                        const int kb = g == 0 ? T.order0[pos] : T.orderH[pos];
-                        const long long c0 = dbg ? clock64() : 0;
-                        ptx::mbar_wait(&x_ready[kb], (xphase >> kb) & 1u);
-                        const long long c1 = dbg ? clock64() : 0;
-                        if (dbg && pos == 0) dbg[0] = c1;
-                        xphase ^= 1u << kb;
-                        ptx::mbar_wait(&w_full[rc.stage], rc.phase);
-                        const long long c2 = dbg ? clock64() : 0;
-                        if (dbg) { xw += c1 - c0; ww += c2 - c1; }
-                        tc::fence_after_sync();
-                        const uint32_t wb = w_a + rc.stage * kMaxStageBytes;
-                        // descriptors: low word = addr >> 4 | LBO >> 4 << 16 ; high word = SBO >> 4 | version
-                        const uint32_t a_lo32 = ((xhi_a + 2 * kb * kXChunkBytes) >> 4) | ((kXChunkBytes >> 4) << 16);
-                        const uint32_t al_lo32 = ((xlo_a + 2 * kb * kXChunkBytes) >> 4) | ((kXChunkBytes >> 4) << 16);
-                        const uint32_t b_lo32 = (wb >> 4) | b_lbo;
-                        const uint32_t bl_lo32 = ((wb + N * 32) >> 4) | b_lbo;
-                        const uint64_t a_hi = ((uint64_t)desc_hi_const << 32) | a_lo32;
-                        const uint64_t a_lo = ((uint64_t)desc_hi_const << 32) | al_lo32;
-                        const uint64_t b_hi = ((uint64_t)desc_hi_const << 32) | b_lo32;
-                        const uint64_t b_lo = ((uint64_t)desc_hi_const << 32) | bl_lo32;
-                        if (ptx::elect_one()) {
+        if (ptx::elect_one()) {
+            Ring rc{0, 0, nstage};
+            uint32_t xphase = 0;          // bit kb = parity to wait for on x_ready[kb]
+            uint32_t g_count = 0;         // running GEMM index: accumulator buffer = g & 1
+            const uint32_t xhi_d = ptx::smem_u32(xhi) >> 4, xlo_d = ptx::smem_u32(xlo) >> 4, w_d = ptx::smem_u32(wring) >> 4;
+            const uint64_t top = (uint64_t)((1u << 14) | 8u) << 32;      // version 1 (bit 46), SBO = 128 B
+            const uint32_t a_lbo = (kXChunkBytes >> 4) << 16;             // A: LBO = one 8-wide k-chunk of all 128 rows
+            for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
+                for (int t = 0; t < P.h; ++t) {
+                    const bool trace = T.dbg && blockIdx.x == 0 && tile == (int)blockIdx.x && t < 64;
+                    for (int g = 0; g < gemms_per_step; ++g) {
+                        const int nkb = g == 0 ? T.nkb0 : T.nkbH;
+                        const uint32_t N = g == P.n_hidden ? (uint32_t)T.NHp : (uint32_t)T.Np;
+                        const uint32_t d_tmem = tmem_base + (g_count & 1u) * 256u;
+                        const uint32_t idesc = tc::idesc_f16(tc::kFmtF16, tc::kFmtF16, N);
+                        const uint32_t b_lbo = N << 16;                   // B: LBO = 16 N bytes
+                        const uint32_t b_lo_off = (N * 32u) >> 4;         // W_lo block behind W_hi
+                        for (int pos = 0; pos < nkb; ++pos) {
+                            const uint32_t kb = g == 0 ? T.order0[pos] : T.orderH[pos];
+                            ptx::mbar_wait(&x_ready[kb], (xphase >> kb) & 1u);
+                            xphase ^= 1u << kb;
+                            ptx::mbar_wait(&w_full[rc.stage], rc.phase);
+                            if (pos == 0) {
+                                tc::fence_after_sync();
+                                if (trace && g < 5) T.dbg[t * 64 + 32 + 4 * g] = clock64();
+                            }
+                            const uint32_t wb = w_d + (uint32_t)rc.stage * (kMaxStageBytes >> 4);
+                            const uint64_t a_hi = top | ((xhi_d + kb * ((2u * kXChunkBytes) >> 4)) | a_lbo);
+                            const uint64_t a_lo = top | ((xlo_d + kb * ((2u * kXChunkBytes) >> 4)) | a_lbo);
+                            const uint64_t b_hi = top | (wb | b_lbo);
+                            const uint64_t b_lo = top | ((wb + b_lo_off) | b_lbo);
                             tc::mma_f16_ss(d_tmem, a_hi, b_hi, idesc, pos > 0 ? 1u : 0u);
                             if (T.terms == 3) {
                                 tc::mma_f16_ss(d_tmem, a_hi, b_lo, idesc, 1u);
                                 tc::mma_f16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
                             }
                             tc::mma_commit(&w_empty[rc.stage]);
+                            rc.advance();
                         }
-                        if (dbg) iw += clock64() - c2;
-                        rc.advance();
+                        tc::mma_commit(&acc_full[g_count & 1u]);
+                        if (trace && g < 5) T.dbg[t * 64 + 33 + 4 * g] = clock64();
+                        ++g_count;
                     }
-                    if (ptx::elect_one()) tc::mma_commit(&acc_full[g_count & 1u]);
-                    if (dbg) { dbg[1] = clock64(); dbg[2] = xw; dbg[3] = ww; T.dbg[t * 64 + 56 + g] = iw; }
-                    ++g_count;
                 }
             }
+            done[1] = 1u;
+        } else {
+            while (!done[1]) __nanosleep(2000);
         }
+        __syncwarp();
     }
     // ======================= warps 2..9: prologue / epilogue ======================================
     else {
