@@ -201,12 +201,15 @@ def run_engine(args, rank, world, local_rank):
     units = 5 * m * n_total * p * h
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
 
+    out_mean = torch.empty_like(dv["init_mean"])
+    out_var = torch.empty_like(dv["init_var"])
+
     def step(i, timed=None):
         seed = (1 << 32) | i
         if timed is not None:
             timed[0].record()
         if world == 1:
-            eng.plan_cem(dv["obs"], dv["init_mean"], dv["init_var"], dv.get("cp_obs"), dv.get("cp_act"), seed=seed, logs=False)
+            eng.plan_cem_into(dv["obs"], dv["init_mean"], dv["init_var"], out_mean, out_var, dv.get("cp_obs"), dv.get("cp_act"), seed=seed)
         else:
             planner.plan(dv["obs"], dv["init_mean"], dv["init_var"], dv.get("cp_obs"), dv.get("cp_act"), seed=seed, logs=False)
         if timed is not None:

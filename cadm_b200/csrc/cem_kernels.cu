@@ -285,7 +285,11 @@ cudaError_t launch_rs_gather(const float* actions, const int* actions_int, const
 // context encoder (core/utils.py:400-407, 591-617): relu hidden layers, linear output; one CTA per (mi, e)
 // ------------------------------------------------------------------------------------------------
 
-__global__ void encoder_kernel(const EncoderParams Q) {
+// One CTA per (environment, member).  A layer is a mat-vec with 10^4..10^5 weights read once from L2: the k range is split
+// over the warps' lanes in groups (kSplit lanes per output unit, partial sums combined with shuffles) so that every thread
+// has several independent loads in flight instead of one 240-deep dependent FMA chain per output (which took ~130 us).
+// The summation order is fixed (per-lane serial, then a butterfly), so the result does not depend on the launch.
+__global__ void __launch_bounds__(512) encoder_kernel(const EncoderParams Q) {
     extern __shared__ float ebuf[];      // two ping-pong vectors of max width
     const int mi = blockIdx.x, e = blockIdx.y;
     int wmax = 0;
@@ -300,16 +304,26 @@ __global__ void encoder_kernel(const EncoderParams Q) {
         x[i] = v;
     }
     __syncthreads();
+    constexpr int kSplit = 8;            // lanes per output unit
+    const int sub = threadIdx.x % kSplit, grp = threadIdx.x / kSplit, ngrp = blockDim.x / kSplit;
     for (int l = 0; l < Q.n_layers; ++l) {
         const int in = Q.dims[l], out = Q.dims[l + 1];
         const float* W = Q.W[l] + (size_t)e * in * out;
         const float* b = Q.b[l] + (size_t)e * out;
-        for (int j = threadIdx.x; j < out; j += blockDim.x) {
+        for (int j0 = 0; j0 < out; j0 += ngrp) {
+            const int j = j0 + grp;
             float acc = 0.f;
-            for (int i = 0; i < in; ++i) acc = fmaf(x[i], W[(size_t)i * out + j], acc);
-            acc += b[j];
-            if (l < Q.n_layers - 1) acc = fmaxf(acc, 0.f);
-            y[j] = acc;
+            if (j < out) {
+#pragma unroll 4
+                for (int i = sub; i < in; i += kSplit) acc = fmaf(x[i], __ldg(W + (size_t)i * out + j), acc);
+            }
+#pragma unroll
+            for (int o = kSplit / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (j < out && sub == 0) {
+                acc += b[j];
+                if (l < Q.n_layers - 1) acc = fmaxf(acc, 0.f);
+                y[j] = acc;
+            }
         }
         __syncthreads();
         float* t = x; x = y; y = t;
@@ -320,7 +334,7 @@ __global__ void encoder_kernel(const EncoderParams Q) {
 cudaError_t launch_encoder(const EncoderParams& Q, cudaStream_t stream) {
     int wmax = 0;
     for (int l = 0; l <= Q.n_layers; ++l) wmax = max(wmax, Q.dims[l]);
-    encoder_kernel<<<dim3(Q.m, Q.E), 256, 2 * wmax * sizeof(float), stream>>>(Q);
+    encoder_kernel<<<dim3(Q.m, Q.E), 512, 2 * wmax * sizeof(float), stream>>>(Q);
     return cudaGetLastError();
 }
 

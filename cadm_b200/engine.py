@@ -205,6 +205,14 @@ class PlannerEngine:
         self._keep = [obs, init_mean, init_var, cp_obs, cp_act, z, eps]
         return dict(mean=mean, var=var, returns=rets, elites=el)
 
+    def plan_cem_into(self, obs, init_mean, init_var, out_mean, out_var, cp_obs=None, cp_act=None, seed=0):
+        """The same decision for callers that keep everything on the device: float32 CUDA tensors in, results written into
+        the caller's `out_mean` / `out_var` [m, h, A]; no conversions, no allocations, no logs (one C call per decision)."""
+        with torch.cuda.device(self.device):
+            self._chk(self.lib.cadm_plan_cem(self._h, obs.shape[0], _ptr(obs), _ptr(cp_obs), _ptr(cp_act), _ptr(init_mean),
+                                             _ptr(init_var), C.c_uint64(seed), None, None, _ptr(out_mean), _ptr(out_var), None, None,
+                                             self._stream()))
+
     def plan_cem_host(self, obs: np.ndarray, init_mean: np.ndarray, init_var: np.ndarray, cp_obs=None, cp_act=None,
                       seed=0) -> np.ndarray:
         """The get_action() path: NumPy in, clipped plan [m,h,A] out; H2D/D2H copies inside the call."""
