@@ -189,8 +189,10 @@ def run_engine(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     n_total = CAND_PER_GPU * world if args.config == "C2" else None
-    model, env, cfg = build_model(args.config, m_max=max(args.m, 1), candidates=n_total, rank=rank, world=world,
-                                  precision=args.precision, device=dev)
+    if args.cand:
+        n_total = args.cand                       # C5 sweep cell: global candidate count as given (strong scaling over GPUs)
+    model, env, cfg = build_model(args.config, m_max=max(args.m, 1), candidates=n_total, particles=args.part or None, rank=rank,
+                                  world=world, precision=args.precision, device=dev)
     if n_total is None:
         n_total = cfg["candidates"]
     eng = model.engine
@@ -320,8 +322,9 @@ def run_engine(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": units * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[args.config] + f", m={m}" + (f", n={n_total} sharded {world} x {n_total // world}" if world > 1 else ""),
+        "scaling": "strong" if args.cand else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": (WORKLOAD_NAMES[args.config] if not (args.cand or args.part) else
+                                f"HalfCheetah PE-TS CEM sweep cell (ens={E}, part={p}, cand={n_total}, horizon={h})") + f", m={m}" + (f", n={n_total} sharded {world} x {n_total // world}" if world > 1 else ""),
                    "precision": args.precision, "kernel": eng.kernel_name,
                    "l2": "flushed between steps (256 MiB write outside the timed events); weights (2.7 MB) are L2-resident by design within a step",
                    "parallelism": (f"candidates sharded over {world} GPU(s), 1 all-gather of [m, n/G] returns per CEM iteration, "
@@ -352,6 +355,8 @@ def main():
     ap.add_argument("--m", type=int, default=1)
     ap.add_argument("--precision", default=os.environ.get("CADM_PRECISION", "tc3x"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cand", type=int, default=0, help="override the candidate count (C5 sweep cells)")
+    ap.add_argument("--part", type=int, default=0, help="override the particle count (C5 sweep cells)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cadm_b200" else args.warmup
 
