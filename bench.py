@@ -42,6 +42,29 @@ def load_peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, src="fallback")
 
 
+def ncu_traffic(kernel_name):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture of the same
+    workload (profiles/*_ncu_summary.csv, written by tools/ncu_summary.py); None when no capture of that kernel is there."""
+    import csv
+    import glob
+    key = kernel_name.split("(")[0]
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units, vals = rows[0], rows[1], rows[2]
+            if key not in vals[hdr.index("Kernel Name")]:
+                continue
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot = 0.0
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(name)
+                tot += float(vals[i].replace(",", "")) * scale.get(units[i], 1.0)
+            return tot, os.path.relpath(path, ROOT)
+        except (ValueError, IndexError, OSError):
+            continue
+    return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -319,6 +342,7 @@ def run_engine(args, rank, world, local_rank):
     units_per_launch = m * (n_total // world) * p * h
     launch_ms = statistics.mean(kernel_ms) / 5.0
     achieved = units_per_launch * fpu / (launch_ms * 1e-3) / 1e12
+    traffic, traffic_src = ncu_traffic(eng.kernel_name) if (world == 1 and args.config == "C2" and m == 1 and not (args.cand or args.part)) else (None, None)
     line = {
         "metric": METRIC, "value": units * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -334,7 +358,7 @@ def run_engine(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_burst"], "traffic": None, "kernel": eng.kernel_name,
+                     "frac": achieved / peaks["bf16_burst"], "traffic": traffic, "traffic_source": traffic_src, "kernel": eng.kernel_name,
                      "launch_ms": launch_ms, "flop_per_unit": fpu, "units_per_launch": units_per_launch,
                      "peak_source": f"{peaks['src']} bf16 dense burst (MEASURED_PEAKS.json)",
                      "kernel_share_of_step": statistics.mean(kernel_ms) / (total_ms / args.steps)},

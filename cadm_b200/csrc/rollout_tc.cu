@@ -39,9 +39,11 @@ constexpr int kMaxKB = 13;                     // K16 blocks of the widest layer
 constexpr int kXChunkBytes = 2048;             // one 8-wide k-chunk of all 128 rows: 128 rows x 16 B
 constexpr int kXBytes = 2 * kMaxKB * kXChunkBytes;   // 53248 per operand half (hi or lo)
 constexpr int kMaxStageBytes = 2 * 208 * 32;   // hi + lo block of one K16 step, N = 208
+constexpr int kBlocksPerStage = 2;             // K16 blocks per ring slot (consecutive in consumption order): half the barrier waits
+constexpr int kSlotBytes = kBlocksPerStage * kMaxStageBytes;
 
 struct TcSmem {
-    size_t off_xhi, off_xlo, off_w, off_s, off_bias, off_vec, off_rowi, off_feat, off_zero, off_act, off_ctx, off_bar, total;
+    size_t off_xhi, off_xlo, off_w, off_s, off_bias, off_vec, off_rowi, off_feat, off_zero, off_act, off_ctx, off_nz, off_bar, total;
     int stages;
 };
 
@@ -50,7 +52,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int D, int A, int C, int n_hidd
     size_t o = 0;
     L.off_xhi = o; o += kXBytes;
     L.off_xlo = o; o += kXBytes;
-    L.off_w = o; o += (size_t)stages * kMaxStageBytes;
+    L.off_w = o; o += (size_t)stages * kSlotBytes;
     L.off_s = o; o += (size_t)round_up(kTileRows * (D + 1), 4) * 4;
     o = (o + 15) / 16 * 16;
     L.off_bias = o; o += (size_t)round_up(n_hidden * Np + NHp, 4) * 4;
@@ -60,6 +62,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int D, int A, int C, int n_hidd
     L.off_zero = o; o += 16;                                     // a zero word (padding features read it)
     L.off_act = o; o += (size_t)2 * kTileRows * A * 4;          // this step's / next step's actions of the tile rows
     L.off_ctx = o; o += (size_t)kTileRows * C * 4;              // context vector of every tile row
+    L.off_nz = o; o += (size_t)kTileRows * ((D + 3) / 4 * 4) * 4;  // this step's N(0,1) draws, [row][4 * Philox blocks]
     o = (o + 15) / 16 * 16;
     L.off_bar = o; o += (size_t)(2 * 8 + kMaxKB + 2 + 2) * 8;     // w_full[8], w_empty[8], x_ready[13], acc_full[2], tmem slot
     L.total = o;
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
     float2* feat_f = reinterpret_cast<float2*>(smem + L.off_feat + 96 * 16);   // {mean, 8 / (std + 1e-10)}
     float* act_s = reinterpret_cast<float*>(smem + L.off_act);
     float* ctx_s = reinterpret_cast<float*>(smem + L.off_ctx);
+    float* nz_s = reinterpret_cast<float*>(smem + L.off_nz);
     uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* w_empty = w_full + 8;
     uint64_t* x_ready = w_empty + 8;
@@ -263,11 +267,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                     for (int g = 0; g < gemms_per_step; ++g) {
                         const int nkb = g == 0 ? T.nkb0 : T.nkbH;
                         const uint32_t bytes = g == P.n_hidden ? stage_bytes_o : stage_bytes_h;
-                        for (int kb = 0; kb < nkb; ++kb) {
+                        for (int kb = 0; kb < nkb; kb += kBlocksPerStage) {          // the image is in consumption order: a stage
+                            const uint32_t sb = bytes * (uint32_t)min(kBlocksPerStage, nkb - kb);   // is one contiguous copy
                             ptx::mbar_wait(&w_empty[rp.stage], rp.phase ^ 1u);
-                            ptx::mbar_arrive_expect_tx(&w_full[rp.stage], bytes);
-                            ptx::bulk_g2s(wring + (size_t)rp.stage * kMaxStageBytes, wsrc + off, bytes, &w_full[rp.stage]);
-                            off += bytes;
+                            ptx::mbar_arrive_expect_tx(&w_full[rp.stage], sb);
+                            ptx::bulk_g2s(wring + (size_t)rp.stage * kSlotBytes, wsrc + off, sb, &w_full[rp.stage]);
+                            off += sb;
                             rp.advance();
                         }
                     }
@@ -306,14 +311,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                         const uint32_t b_lo_off = (N * 32u) >> 4;         // W_lo block behind W_hi
                         for (int pos = 0; pos < nkb; ++pos) {
                             const uint32_t kb = g == 0 ? T.order0[pos] : T.orderH[pos];
+                            const int sub = pos % kBlocksPerStage;               // block within the ring slot
                             ptx::mbar_wait(&x_ready[kb], (xphase >> kb) & 1u);
                             xphase ^= 1u << kb;
-                            ptx::mbar_wait(&w_full[rc.stage], rc.phase);
+                            if (sub == 0) ptx::mbar_wait(&w_full[rc.stage], rc.phase);
                             if (pos == 0) {
                                 tc::fence_after_sync();
                                 if (trace && g < 5) T.dbg[t * 64 + 32 + 4 * g] = clock64();
                             }
-                            const uint32_t wb = w_d + (uint32_t)rc.stage * (kMaxStageBytes >> 4);
+                            const uint32_t wb = w_d + (uint32_t)rc.stage * (kSlotBytes >> 4) + (uint32_t)sub * ((N * 64u) >> 4);
                             const uint64_t a_hi = top | ((xhi_d + kb * ((2u * kXChunkBytes) >> 4)) | a_lbo);
                             const uint64_t a_lo = top | ((xlo_d + kb * ((2u * kXChunkBytes) >> 4)) | a_lbo);
                             const uint64_t b_hi = top | (wb | b_lbo);
@@ -323,8 +329,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                                 tc::mma_f16_ss(d_tmem, a_hi, b_lo, idesc, 1u);
                                 tc::mma_f16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
                             }
-                            tc::mma_commit(&w_empty[rc.stage]);
-                            rc.advance();
+                            if (sub == kBlocksPerStage - 1 || pos == nkb - 1) {
+                                tc::mma_commit(&w_empty[rc.stage]);
+                                rc.advance();
+                            }
                         }
                         tc::mma_commit(&acc_full[g_count & 1u]);
                         if (trace && g < 5) T.dbg[t * 64 + 33 + 4 * g] = clock64();
@@ -531,6 +539,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                         if (kb == kb0 && group + 1 < kEpiGroups) ptx::bar_arrive(2 + group, 256);
                     }
                     if (dbg && l < 4) dbg[3 + 2 * l] = clock64();
+                    // off the critical path (the warps wait for the next accumulator anyway): this step's Gaussian draws
+                    if (l == 0 && !P.deterministic) {
+                        const int nj = (D + 3) >> 2;
+                        for (int i = et; i < kTileRows * nj; i += kEpiThreads) {
+                            const int jb = i / kTileRows, r = i - jb * kTileRows;
+                            float nz[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (r < nrows) {
+                                if (P.eps != nullptr) {
+                                    const float* ep = P.eps + (P.row_mode == kRowsPlanner ? (size_t)t * eps_step_stride : 0) + (size_t)r_eps[r] * D;
+#pragma unroll
+                                    for (int ii = 0; ii < 4; ++ii) nz[ii] = 4 * jb + ii < D ? __ldg(ep + 4 * jb + ii) : 0.f;
+                                } else {
+                                    normal4_fast(P.seed, (uint32_t)jb, (uint32_t)r_rid[r], (uint32_t)t, (uint32_t)P.it, nz);
+                                }
+                            }
+                            *reinterpret_cast<float4*>(nz_s + r * (nj * 4) + 4 * jb) = make_float4(nz[0], nz[1], nz[2], nz[3]);
+                        }
+                    }
                 }
 
                 // ---------- heads -> Hd (aliases X_hi once the head GEMM has completed) ------------------
@@ -565,19 +591,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                     const int dper = (D + kEpiGroups - 1) / kEpiGroups;
                     const int d0 = part * dper, d1 = min(D, d0 + dper);
                     if (r < nrows && d0 < d1) {
-                        float nzv[16];                                          // normals of the Philox blocks covering [d0, d1)
-                        const int j0 = d0 >> 2, j1 = (d1 - 1) >> 2;             // at most 4 blocks (dper <= 12)
-                        if (!P.deterministic) {
-                            if (P.eps != nullptr) {
-                                const float* ep = P.eps + (P.row_mode == kRowsPlanner ? (size_t)t * eps_step_stride : 0) + (size_t)r_eps[r] * D;
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) nzv[i] = (4 * j0 + i < D && 4 * j0 + i < d1) ? __ldg(ep + 4 * j0 + i) : 0.f;
-                            } else {
-#pragma unroll
-                                for (int jb = 0; jb < 4; ++jb)
-                                    if (j0 + jb <= j1) normal4_fast(P.seed, (uint32_t)(j0 + jb), (uint32_t)r_rid[r], (uint32_t)t, (uint32_t)P.it, &nzv[4 * jb]);
-                            }
-                        }
+                        const float* nzr = nz_s + r * (((D + 3) >> 2) * 4);         // drawn while layer 1 was running
 #pragma unroll
                         for (int i = 0; i < 12; ++i) {
                             const int d = d0 + i;
@@ -588,7 +602,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                             float delta = dmu;
                             if (!P.deterministic) {
                                 lv = fast_bounded_logvar(lv, v_maxlv[d], v_minlv[d]);
-                                delta = dmu + nzv[d - 4 * j0] * fast_exp((lv + v_2logstd[d]) * 0.5f);
+                                delta = dmu + nzr[d] * fast_exp((lv + v_2logstd[d]) * 0.5f);
                             }
                             float* sp = S + r * (D + 1) + d;
                             const float sn = env_postproc(P.env_id, *sp, delta, d);
@@ -646,7 +660,7 @@ cudaError_t launch_rollout_tc(RolloutParams P, const unsigned char* wimg, long l
     for (int i = 0; i < T.nkb0; ++i) T.order0[i] = (unsigned char)blk_of_pos(T.nkb0, i);
     for (int i = 0; i < T.nkbH; ++i) T.orderH[i] = (unsigned char)blk_of_pos(T.nkbH, i);
     // shared-memory ring: as many stages as fit in 227 KB
-    int stages = 8;
+    int stages = 4;
     while (stages > 2 && tc_smem_layout(P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, stages).total > 226 * 1024) --stages;
     T.stages = stages;
     const TcSmem L = tc_smem_layout(P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, stages);

@@ -1,6 +1,6 @@
 set -x
 cd $GRAFT_REPO_ROOT
-for cand in 200 1000 5000; do for part in 20 100; do
-timeout -k 5 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --cand $cand --part $part 2>/dev/null | tail -1 >> gpurun_out/r1_sweep_c5.jsonl
-done; done
-cat gpurun_out/r1_sweep_c5.jsonl
+timeout -k 5 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tc.py -x -q -k "tiles or tc_gemm" 2>&1 | tail -4
+CADM_TC_VARIANT=1 timeout -k 5 300 python tools/tc_trace.py tc3x 2>&1 | tail -4
+timeout -k 5 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --config C4
+timeout -k 5 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --config C2 --m 10
