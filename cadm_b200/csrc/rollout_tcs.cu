@@ -146,6 +146,16 @@ __device__ __forceinline__ void store_rows8(unsigned char* xhi, unsigned char* x
     *reinterpret_cast<uint4*>(xlo + o) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// sin / cos with a two-constant Cody-Waite reduction to [-pi, pi] and the MUFU approximations (|error| ~ 1e-6 for |x| up to a few
+// hundred; the accurate sincosf costs ~350 cycles on the per-step critical path)
+__device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, x);          // 2 pi rounded to fp32 ...
+    r = fmaf(k, 1.7484556000744883e-07f, r);             // ... and its remainder
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(r));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(r));
+}
+
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -497,6 +507,12 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
         const int cslice = ew >> 2;                    // the warp takes the 8-column (8 batch rows) chunks cslice, cslice + 4, ...
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int nchunks = N >> 3;
+        // the warps whose TMEM lane quarter holds no head output are idle in the head epilogue: they prefetch the next step's
+        // actions and build its action / context features there, off the critical path
+        const int nq_head = (T.NHp + 31) >> 5;
+        const bool helper = quarter >= nq_head;
+        const int n_help = 128 * (4 - nq_head);                                  // 0 when the heads fill all four quarters
+        const int ht = ((quarter - nq_head) + (4 - nq_head) * cslice) * 32 + lane;    // index among the helper threads
         uint32_t g_count = 0;                          // GEMMs so far   = completions of acc_full[0]
         uint32_t c1cnt = 0;                            // 2-tile GEMMs   = completions of acc_full[1]
         unsigned char* const x0hi = xbuf;              // layer-input buffer 0 (layer 0 and every other layer after it)
@@ -580,10 +596,10 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 const int r = i / P.C, c = i - r * P.C;
                 ctx_s[i] = r < nrows ? __ldg(P.ctx + (size_t)r_ctx[r] * P.C + c) : 0.f;
             }
-            auto prefetch_actions = [&](int t) {
+            auto prefetch_actions = [&](int t, int first, int stride) {
                 if (P.discrete && P.row_mode == kRowsPlanner) return;
                 float* dst = act_s + (t & 1) * N * A;
-                for (int i = et; i < nrows * A; i += kSEpiThreads) {
+                for (int i = first; i < nrows * A; i += stride) {
                     const int r = i / A, a = i - r * A;
                     tcs::cp_async4(dst + i, P.actions + ((size_t)r_src[r] * P.h + t) * A + a);
                 }
@@ -592,57 +608,61 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
             for (int i = et; i < 2 * N * A; i += kSEpiThreads) act_s[i] = 0.f;   // rows >= nrows stay finite
             ptx::bar_sync(1, kSEpiThreads);
             if (P.env_id == CADM_ENV_HALFCHEETAH && et < N) sincosf(S[et * (D + 3) + 2], &S[et * (D + 3) + D + 1], &S[et * (D + 3) + D + 2]);
-            prefetch_actions(0);
+            prefetch_actions(0, et, kSEpiThreads);
             tcs::cp_async_wait_all();
             ptx::bar_sync(1, kSEpiThreads);
 
             float ret = 0.f;                               // return of row `et` (threads et < nrows)
+            const bool onehot_mode = P.discrete && P.row_mode == kRowsPlanner;
+            const bool is_hc = P.env_id == CADM_ENV_HALFCHEETAH;
+            const int kf_shift = P.env_id == CADM_ENV_ANT ? -1 : 0;       // obs_preproc: Ant drops o[0]
+            const bool want_out = P.states != nullptr || P.next_obs != nullptr || P.mu_out != nullptr || P.lv_out != nullptr;
+            // layer-0 input features k in [k_lo, K0) of step t for every row, from the state / the step's actions / the
+            // context; one work item = (feature, pair of rows), 4-byte stores into the MN-major layout
+            auto build_features = [&](int t, int k_lo, int first, int stride) {
+                const int par_off = (t & 1) * N * A * 4;
+                const int nk = K0 - k_lo;
+                for (int i = first; i < nk * (N >> 1); i += stride) {
+                    const int rp = i / nk, k = k_lo + (i - rp * nk);
+                    const int4 fi = feat_i[k];
+                    const float2 ff = feat_f[k];
+                    float y[2];
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int r = rp * 2 + jj;
+                        float src = *reinterpret_cast<const float*>(smem + fi.x + r * fi.y + ((fi.z & 1) ? par_off : 0));
+                        if (onehot_mode && (fi.z & 1)) {
+                            const int oh = r < nrows ? __ldg(P.actions_int + (size_t)r_src[r] * P.h + t) : -1;
+                            src = (oh == k - P.P) ? 1.f : 0.f;
+                        }
+                        y[jj] = r < nrows ? (src - ff.x) * ff.y : 0.f;
+                    }
+                    uint32_t hq, lq;
+                    tc::split2(y[0], y[1], hq, lq);
+                    const int o = (rp >> 2) * xsbo + (k >> 3) * 128 + (k & 7) * 16 + (rp & 3) * 4;
+                    *reinterpret_cast<uint32_t*>(x0hi + o) = hq;
+                    *reinterpret_cast<uint32_t*>(x0hi + L.xbytes + o) = lq;
+                }
+            };
+            // hand the layer-0 input to the MMA thread (generic-proxy writes -> async-proxy reads)
+            auto publish_input = [&]() {
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { ptx::mbar_arrive(&xr[0]); ptx::mbar_arrive(&xr[1]); }
+            };
+            // reward terms of step t that read the CURRENT observation and the action (quirk Q4); threads et < nrows
+            auto add_reward = [&](int t) {
+                if (et < nrows && !env_reward_reads_next(P.env_id))
+                    ret += env_reward_current(P.env_id, S + et * (D + 3), act_s + (t & 1) * N * A + et * A, A, P.max_torque);
+            };
+            // step 0: everything from the start state
+            build_features(0, 0, et, kSEpiThreads);
+            publish_input();
+            add_reward(0);
 #pragma unroll 1
             for (int t = 0; t < P.h; ++t) {
                 long long* dbg = (T.dbg && blockIdx.x == 0 && ew == 2 && lane == 0 && tile == (int)blockIdx.x && t < 64) ? T.dbg + t * 64 : nullptr;
                 if (dbg) dbg[0] = clock64();
-                // ---------- prologue: reward of the current state; layer-0 input ------------------------
-                if (et < nrows) {
-                    const float* s = S + et * (D + 3);
-                    const float* arow = act_s + (t & 1) * N * A + et * A;
-                    if (env_reward_reads_next(P.env_id)) {
-                        if (t > 0) ret += env_reward_next(P.env_id, s);
-                    } else {
-                        ret += env_reward_current(P.env_id, s, arow, A, P.max_torque);
-                    }
-                }
-                if (dbg) dbg[13] = clock64();
-                {
-                    const int par_off = (t & 1) * N * A * 4;
-                    const bool onehot_mode = P.discrete && P.row_mode == kRowsPlanner;
-                    // one work item = (feature k, pair of rows): 512 items for 32 features x 32 rows, one short chain per thread
-                    // (8 rows per thread was a ~900-cycle dependent chain on 128 threads); 4-byte stores into the MN-major layout
-                    for (int i = et; i < K0 * (N >> 1); i += kSEpiThreads) {
-                        const int rp = i / K0, k = i - rp * K0;
-                        const int4 fi = feat_i[k];
-                        const float2 ff = feat_f[k];
-                        float y[2];
-#pragma unroll
-                        for (int jj = 0; jj < 2; ++jj) {
-                            const int r = rp * 2 + jj;
-                            float src = *reinterpret_cast<const float*>(smem + fi.x + r * fi.y + ((fi.z & 1) ? par_off : 0));
-                            if (onehot_mode && (fi.z & 1)) {
-                                const int oh = r < nrows ? __ldg(P.actions_int + (size_t)r_src[r] * P.h + t) : -1;
-                                src = (oh == k - P.P) ? 1.f : 0.f;
-                            }
-                            y[jj] = r < nrows ? (src - ff.x) * ff.y : 0.f;
-                        }
-                        uint32_t hq, lq;
-                        tc::split2(y[0], y[1], hq, lq);
-                        const int o = (rp >> 2) * xsbo + (k >> 3) * 128 + (k & 7) * 16 + (rp & 3) * 4;
-                        *reinterpret_cast<uint32_t*>(x0hi + o) = hq;
-                        *reinterpret_cast<uint32_t*>(x0hi + L.xbytes + o) = lq;
-                    }
-                    if (dbg) dbg[14] = clock64();
-                    ptx::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) { ptx::mbar_arrive(&xr[0]); ptx::mbar_arrive(&xr[1]); }
-                }
                 if (dbg) dbg[1] = clock64();
                 // ---------- hidden layers: accumulator -> bias + swish -> next layer's B operand ----------
 #pragma unroll 1
@@ -699,7 +719,10 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                     // ---------- off the critical path: the warps are idle from here until the next layer's first accumulator is
                     // ready: next step's actions, this step's noise
                     if (l == 0) {
-                        if (t + 1 < P.h) prefetch_actions(t + 1);
+                        if (t + 1 < P.h) {
+                            if (n_help == 0) prefetch_actions(t + 1, et, kSEpiThreads);
+                            else if (helper) prefetch_actions(t + 1, ht, n_help);
+                        }
                         if (!P.deterministic) {
                             for (int i = et; i < N * nj; i += kSEpiThreads) {
                                 const int jb = i / N, r = i - jb * N;
@@ -754,8 +777,16 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                             }
                         }
                         tc::fence_before_sync();
+                    } else if (t + 1 < P.h) {
+                        // helper warps: buffer 0 is free once the head GEMM has read it; the next step's actions were prefetched by
+                        // these same threads
+                        ptx::mbar_wait(&acc_full[0], par0);
+                        tcs::cp_async_wait_all();
+                        ptx::bar_sync(2, n_help);
+                        build_features(t + 1, P.P, ht, n_help);
                     }
                 }
+                tcs::cp_async_wait_all();                  // next step's actions have landed (prefetched after layer 0)
                 ptx::bar_sync(1, kSEpiThreads);
                 if (dbg) dbg[11] = clock64();
 
@@ -774,25 +805,70 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                     float* sp = S + r * (D + 3) + d;
                     const float sn = env_postproc(P.env_id, *sp, delta, d);
                     *sp = sn;
-                    if (P.env_id == CADM_ENV_HALFCHEETAH && d == 2) sincosf(sn, sp + (D + 1 - 2), sp + (D + 2 - 2));   // next step's features
-                    if (P.row_mode == kRowsPlanner) {
-                        if (P.states != nullptr)
-                            P.states[(((size_t)t * P.m * P.n_local + r_src[r]) * P.p + r_pi[r]) * D + d] = sn;
-                    } else {
-                        const size_t o = (size_t)r_src[r] * D + d;
-                        if (P.next_obs) P.next_obs[o] = sn;
-                        if (P.mu_out) P.mu_out[o] = mu;
-                        if (P.lv_out) P.lv_out[o] = lv;
+                    // the next step's layer-0 input straight from here: state dim d is processed-observation feature kf
+                    // (obs_preproc: HalfCheetah [o1, sin o2, cos o2, o3:], Ant o[1:], identity otherwise)
+                    if (t + 1 < P.h) {
+                        int kf = d + kf_shift;
+                        float f0 = sn, f1 = 0.f;
+                        bool two = false;
+                        if (is_hc) {
+                            if (d <= 1) kf = d - 1;
+                            else if (d == 2) { tcs::sincos_reduced(sn, f0, f1); kf = 1; two = true; }
+                        }
+                        if (kf >= 0) {
+                            const int ob = (r >> 3) * xsbo + (r & 7) * 2;
+                            const float2 ff = feat_f[kf];
+                            uint32_t hq, lq;
+                            tc::split2((f0 - ff.x) * ff.y, 0.f, hq, lq);
+                            const int o = ob + (kf >> 3) * 128 + (kf & 7) * 16;
+                            *reinterpret_cast<unsigned short*>(x0hi + o) = (unsigned short)hq;
+                            *reinterpret_cast<unsigned short*>(x0hi + L.xbytes + o) = (unsigned short)lq;
+                            if (two) {
+                                const float2 fg = feat_f[kf + 1];
+                                tc::split2((f1 - fg.x) * fg.y, 0.f, hq, lq);
+                                const int o1 = ob + ((kf + 1) >> 3) * 128 + ((kf + 1) & 7) * 16;
+                                *reinterpret_cast<unsigned short*>(x0hi + o1) = (unsigned short)hq;
+                                *reinterpret_cast<unsigned short*>(x0hi + L.xbytes + o1) = (unsigned short)lq;
+                            }
+                        }
+                    }
+                    if (want_out) {                          // trajectories / one-step outputs were asked for (tests, predict)
+                        if (P.row_mode == kRowsPlanner) {
+                            if (P.states != nullptr)
+                                P.states[(((size_t)t * P.m * P.n_local + r_src[r]) * P.p + r_pi[r]) * D + d] = sn;
+                        } else {
+                            const size_t o = (size_t)r_src[r] * D + d;
+                            if (P.next_obs) P.next_obs[o] = sn;
+                            if (P.mu_out) P.mu_out[o] = mu;
+                            if (P.lv_out) P.lv_out[o] = lv;
+                        }
                     }
                 }
-                tcs::cp_async_wait_all();                  // next step's actions have landed (issued at the top of the step)
-                ptx::bar_sync(1, kSEpiThreads);
+                if (dbg) dbg[13] = clock64();
+                if (t + 1 < P.h) {
+                    // rows beyond the tile (zero features) and the action / context / padding features of the next step
+                    if (nrows < N) {
+                        for (int i = et; i < (N - nrows) * P.P; i += kSEpiThreads) {
+                            const int r = nrows + i / P.P, kf = i % P.P;
+                            const int o = (r >> 3) * xsbo + (r & 7) * 2 + (kf >> 3) * 128 + (kf & 7) * 16;
+                            *reinterpret_cast<unsigned short*>(x0hi + o) = 0;
+                            *reinterpret_cast<unsigned short*>(x0hi + L.xbytes + o) = 0;
+                        }
+                    }
+                    if (n_help == 0) build_features(t + 1, P.P, et, kSEpiThreads);
+                    publish_input();
+                }
+                if (dbg) dbg[14] = clock64();
+                ptx::bar_sync(1, kSEpiThreads);            // the new state is complete and visible
+                if (dbg) dbg[15] = clock64();
+                if (env_reward_reads_next(P.env_id)) {
+                    if (et < nrows) ret += env_reward_next(P.env_id, S + et * (D + 3));
+                } else if (t + 1 < P.h) {
+                    add_reward(t + 1);
+                }
                 if (dbg) dbg[12] = clock64();
             }
-            if (P.row_mode == kRowsPlanner && et < nrows) {
-                if (env_reward_reads_next(P.env_id)) ret += env_reward_next(P.env_id, S + et * (D + 3));
-                P.ret_p[(size_t)r_src[et] * P.p + r_pi[et]] = ret;
-            }
+            if (P.row_mode == kRowsPlanner && et < nrows) P.ret_p[(size_t)r_src[et] * P.p + r_pi[et]] = ret;
         }
     }
 
