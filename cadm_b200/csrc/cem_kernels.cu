@@ -148,10 +148,17 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
     float* el = reinterpret_cast<float*>(keys + R.npad);
     if (R.peer_flags != nullptr) {
         // fused all-gather: wait until every rank's slice of this iteration has landed in OUR returns buffer
+        // (bounded: a rank that died must not leave the others spinning on the GPU for ever -- after ~4e9 cycles, about two
+        // seconds, the wait gives up and reports through the host-mapped word; the host raises on the next call)
         if (tid < R.world) {
             int seen;
+            const long long t0 = clock64();
             do {
                 asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(R.peer_flags + tid) : "memory");
+                if (seen - R.peer_epoch < 0 && clock64() - t0 > 4000000000ll) {
+                    if (R.peer_timeout) *reinterpret_cast<volatile int*>(R.peer_timeout) = 1 + tid;
+                    break;
+                }
             } while (seen - R.peer_epoch < 0);
         }
         __syncthreads();

@@ -67,6 +67,8 @@ struct Engine {
     std::vector<void*> peer_open;            // mappings to close
     bool peers_on = false;
     int epoch = 0;                           // exchange epoch: one per rollout since the peers were attached
+    int* peer_timeout_host = nullptr;        // host-mapped word: a refit kernel gave up waiting for a peer's slice
+    int* peer_timeout_dev = nullptr;
     int* elites_log = nullptr;
     int* best = nullptr;
     // sampler-side state kept on the device (cadm_session_*)
@@ -137,6 +139,17 @@ int check_ready(Engine* E, bool need_encoder) {
     if (!E->have_norm) return fail(E, CADM_ERR_STATE, "cadm_plan_set_norm has not been called");
     if (need_encoder && E->cfg.ctx_dim > 0 && !E->have_encoder)
         return fail(E, CADM_ERR_STATE, "cadm_plan_set_encoder has not been called");
+    return CADM_OK;
+}
+
+// The refit kernel's wait for a peer's slice is bounded; when it gave up it says so in a host-mapped word.  The launches are
+// asynchronous, so the report surfaces on the first engine call after the kernel has run (begin / rollout / finish).
+int check_peers(Engine* E) {
+    if (E->peer_timeout_host && *reinterpret_cast<volatile int*>(E->peer_timeout_host) != 0) {
+        const int who = *E->peer_timeout_host - 1;
+        return fail(E, CADM_ERR_CUDA, "fused all-gather: gave up waiting for the returns slice of rank " + std::to_string(who) +
+                                          " (peer process gone or out of lockstep); results since then are invalid");
+    }
     return CADM_OK;
 }
 
@@ -322,6 +335,7 @@ int cadm_plan_destroy(void* handle) {
     if (!E) return CADM_ERR_ARG;
     cudaDeviceSynchronize();
     for (void* p : E->peer_open) cudaIpcCloseMemHandle(p);
+    if (E->peer_timeout_host) cudaFreeHost(E->peer_timeout_host);
     for (void* p : E->allocs) cudaFree(p);
     for (cudaEvent_t ev : E->ev) cudaEventDestroy(ev);
     delete E;
@@ -498,6 +512,7 @@ int cadm_cem_begin(void* handle, int32_t m, const float* obs, const float* cp_ob
     Engine* E = H(handle);
     if (!E) return CADM_ERR_ARG;
     if (int r = check_ready(E, true)) return r;
+    if (int r = check_peers(E)) return r;
     const CadmConfig& c = E->cfg;
     if (c.discrete) return fail(E, CADM_ERR_UNSUPPORTED, "CEM needs continuous actions (the reference builds RS for discrete envs)");
     if (m < 1 || m > c.m_max) return fail(E, CADM_ERR_ARG, "m out of range (1..m_max)");
@@ -588,6 +603,7 @@ static int refit_common(Engine* E, int it, uint64_t seed, const float* z, cudaSt
         R.returns_buf = reinterpret_cast<const float*>(E->xchg + par * E->xchg_ret_bytes);
         R.peer_flags = reinterpret_cast<const int*>(E->xchg + 2 * E->xchg_ret_bytes + par * 256 * ((c.world * sizeof(int) + 255) / 256));
         R.peer_epoch = E->epoch;
+        R.peer_timeout = E->peer_timeout_dev;
     }
     R.z = z ? z + (size_t)it * m * c.candidates * E->hA : nullptr;
     R.mean = E->mean; R.var = E->var;
@@ -612,6 +628,7 @@ int cadm_cem_finish(void* handle, float* mean, float* var, float* returns, int32
     Engine* E = H(handle);
     if (!E) return CADM_ERR_ARG;
     if (!E->in_flight) return fail(E, CADM_ERR_STATE, "cadm_cem_begin has not been called");
+    if (int r = check_peers(E)) { E->in_flight = false; return r; }
     const CadmConfig& c = E->cfg;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t m = E->m;
@@ -841,6 +858,11 @@ int cadm_peer_attach(void* handle, const void* ipc_handles, int32_t count) {
         }
         E->peer_open.push_back(p);
         tab[r] = reinterpret_cast<unsigned char*>(p);
+    }
+    if (!E->peer_timeout_host) {
+        CU(E, cudaHostAlloc(reinterpret_cast<void**>(&E->peer_timeout_host), sizeof(int), cudaHostAllocMapped));
+        *E->peer_timeout_host = 0;
+        CU(E, cudaHostGetDevicePointer(reinterpret_cast<void**>(&E->peer_timeout_dev), E->peer_timeout_host, 0));
     }
     CU(E, cudaMemcpy(E->peer_tab, tab.data(), sizeof(unsigned char*) * c.world, cudaMemcpyHostToDevice));
     CU(E, cudaMemset(E->xchg + 2 * E->xchg_ret_bytes, 0, E->xchg_bytes - 2 * E->xchg_ret_bytes));      // flags: epoch 0

@@ -35,6 +35,7 @@ struct RefitParams {
     int stage_elites;               // set by the launcher: elite rows fit in shared memory
     const int* peer_flags;          // nullable: [world] arrival epochs written by the peers (fused peer-memory all-gather)
     int peer_epoch;                 // wait until every peer_flags[r] >= peer_epoch before reading returns_buf
+    int* peer_timeout;              // host-mapped word set to 1 + rank-waited-for when the wait gives up (a peer died)
     // random shooting (mode_rs): argmax only
     int mode_rs;
     int* best;                      // [m]

@@ -261,3 +261,64 @@ def test_size_independent_properties_full_size(precision):
             assert r[-1] >= np.sort(rets[it, mi])[::-1][49] - 0.0
     act = model.get_action(inp["obs"], inp["init_mean"], inp["init_var"])
     assert act.shape == (4, 30, 6) and act.dtype == np.float32 and np.abs(act).max() <= 1.0
+
+
+def test_many_candidates_sort_path_and_sharding():
+    """n = 1600 candidates (8 x 200, the 8-GPU weak-scaling size): the elite selection takes the bitonic-sort path (n above the
+    CTA size) and must still return the oracle's indices; eight virtual ranks of 200 give the single-rank bits."""
+    from cadm_b200.dynamics.mlp_ensemble_cem_dynamics import MLPEnsembleCEMDynamicsModel
+    from cadm_b200.envs import make_env
+    from cadm_b200.synth import synthetic_inputs, synthetic_normalization
+    import os
+    old = os.environ.get("CADM_TC_VARIANT")
+    os.environ["CADM_TC_VARIANT"] = "2"
+    try:
+        env = make_env("halfcheetah")
+        n, h, p, E, m = 1600, 4, 5, 5, 1
+
+        def mk(rank=0, world=1):
+            mdl = MLPEnsembleCEMDynamicsModel("dm", env, hidden_nonlinearity="swish", n_forwards=h, n_candidates=n, ensemble_size=E,
+                                              n_particles=p, use_cem=True, m_max=m, precision="tc3x", rank=rank, world=world, seed=3)
+            mdl._dyn["b_lv"][...] = -6.0
+            mdl._push_params()
+            mdl.set_normalization(synthetic_normalization(env, False))
+            return mdl
+        single = mk()
+        prm, enc, norm, oenv = oracle_pack(single)
+        inp = synthetic_inputs(env, m, h, False, seed=11)
+        D, A = env.obs_dim, env.act_dim
+        z = ph.gen_z(5, orc.NUM_CEM_ITERS, m, n, h, A)
+        eps = ph.gen_eps(5, orc.NUM_CEM_ITERS, h, m, n, p, E, D)
+        ref = orc.cem_plan(inp["obs"].astype(np.float64), inp["init_mean"].astype(np.float64), inp["init_var"].astype(np.float64),
+                           z.astype(np.float64), prm, norm, oenv, E, p, False, eps.astype(np.float64))
+        out = single.engine.plan_cem(inp["obs"], inp["init_mean"], inp["init_var"], seed=0, z=z, eps=eps)
+        rets, el = out["returns"].cpu().numpy(), out["elites"].cpu().numpy()
+        for it in range(orc.NUM_CEM_ITERS):
+            assert np.max(np.abs(rets[it] - ref.returns[it])) / np.max(np.abs(ref.returns[it])) < TOL
+            ok, gap, e = elite_margin_ok(ref.returns[it], ref.elites[it], rets[it], orc.NUM_ELITES)
+            if ok:
+                assert np.array_equal(el[it], ref.elites[it]), it
+        assert np.max(np.abs(out["mean"].cpu().numpy() - ref.mean)) < TOL
+        # eight virtual ranks (seed-only noise: every rank regenerates the elites it does not own)
+        G = 8
+        ref2 = single.engine.plan_cem(inp["obs"], inp["init_mean"], inp["init_var"], seed=21)
+        ranks = [mk(r, G) for r in range(G)]
+        for r in ranks:
+            r.engine.cem_begin(inp["obs"], inp["init_mean"], inp["init_var"])
+        for it in range(orc.NUM_CEM_ITERS):
+            for r in ranks:
+                r.engine.cem_rollout(it, seed=21)
+            bufs = [r.engine.returns_buffer() for r in ranks]
+            for i, bi in enumerate(bufs):
+                for j, bj in enumerate(bufs):
+                    if i != j:
+                        bi[j].copy_(bj[j])
+            for r in ranks:
+                r.engine.cem_refit(it)
+        for o in [r.engine.cem_finish() for r in ranks]:
+            assert torch.equal(o["elites"], ref2["elites"]) and torch.equal(o["mean"], ref2["mean"]) and torch.equal(o["returns"], ref2["returns"])
+    finally:
+        if old is None:
+            os.environ.pop("CADM_TC_VARIANT", None)
+        else:
+            os.environ["CADM_TC_VARIANT"] = old
