@@ -203,3 +203,26 @@ def test_session_matches_host_loop(config):
     session.reset(idx=[0])
     p, ho, ha, cnt = session.state()
     assert not p[0].any() and not ho[0].any() and cnt[0] == 0 and p[2].any()
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_tc1x_fast_mode_runs_and_is_fp16_class(variant, monkeypatch):
+    """`precision="tc1x"` (single fp16 pass, does NOT claim the 1e-4 bar) on both tensor-core kernels: finite, and within
+    the fp16-class error one expects from 10-bit operands over an 8-step rollout."""
+    from oracle import cadm_oracle as orc
+    from oracle import philox as ph
+    from helpers import oracle_pack
+    monkeypatch.setenv("CADM_TC_VARIANT", variant)
+    model, env = _pets("halfcheetah", "tc1x", n=64, h=8)
+    prm, enc, norm, oenv = oracle_pack(model)
+    rng = np.random.default_rng(0)
+    m, n, h, p, E = 2, 64, 8, 10, 5
+    obs = (0.1 * rng.standard_normal((m, env.obs_dim))).astype(np.float32)
+    actions = rng.uniform(-1, 1, (m, n, h, env.act_dim)).astype(np.float32)
+    eps = ph.gen_eps(5, 1, h, m, n, p, E, env.obs_dim)[0]
+    o_ret, _ = orc.rollout(obs.astype(np.float64), actions.astype(np.float64), prm, norm, oenv, E, p, False, eps.astype(np.float64), None)
+    pr, _ = model.engine.rollout(obs, actions, None, eps)
+    pr = pr.cpu().numpy()
+    assert np.isfinite(pr).all()
+    err = np.max(np.abs(pr - o_ret)) / np.max(np.abs(o_ret))
+    assert err < 2e-2, err
