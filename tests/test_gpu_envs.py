@@ -226,3 +226,23 @@ def test_tc1x_fast_mode_runs_and_is_fp16_class(variant, monkeypatch):
     assert np.isfinite(pr).all()
     err = np.max(np.abs(pr - o_ret)) / np.max(np.abs(o_ret))
     assert err < 2e-2, err
+
+
+@pytest.mark.parametrize("precision,variant", [("fp32", "0"), ("tc3x", "1"), ("tc3x", "2")])
+@pytest.mark.parametrize("hidden", [(64, 64), (128, 128, 128), (96, 96, 96, 96, 96), (200, 200), (208,)])
+def test_other_architectures(hidden, precision, variant, monkeypatch):
+    """Hidden widths / depths other than the reference's 4 x 200 (one M tile instead of two, widths that are not a multiple of
+    16, 1..5 hidden layers): the table-driven schedules of both tensor-core kernels and the FFMA path against the oracle."""
+    monkeypatch.setenv("CADM_TC_VARIANT", variant)
+    model, env = _pets("halfcheetah", precision, n=64, h=6, hidden_sizes=hidden)
+    prm, enc, norm, oenv = oracle_pack(model)
+    rng = np.random.default_rng(1)
+    m, n, h, p, E = 2, 64, 6, 10, 5
+    obs = (0.1 * rng.standard_normal((m, env.obs_dim))).astype(np.float32)
+    actions = rng.uniform(-1, 1, (m, n, h, env.act_dim)).astype(np.float32)
+    eps = ph.gen_eps(7, 1, h, m, n, p, E, env.obs_dim)[0]
+    o_ret, o_st = orc.rollout(obs.astype(np.float64), actions.astype(np.float64), prm, norm, oenv, E, p, False, eps.astype(np.float64),
+                              None, trace=True)
+    pr, st = model.engine.rollout(obs, actions, None, eps, trace=True)
+    assert rel_err(st.cpu().numpy(), o_st, axis=(1, 2, 3)) < TOL
+    assert np.max(np.abs(pr.cpu().numpy() - o_ret)) / np.max(np.abs(o_ret)) < TOL
