@@ -13,8 +13,8 @@
 //                hidden unit (TMEM lane) and writes 8 consecutive rows as one 16-byte store.  X_lo is laid out directly
 //                behind X_hi at the same 8-row-group stride, so ONE MMA with N = 2 x rows multiplies a weight block by
 //                [X_hi ; X_lo] (the weight block -- 4 KB, the dominant shared-memory fetch of a small-N MMA -- is read once)
-//   precision  = fp16 hi/lo split, the same three products as rollout_tc.cu, kept in three accumulator column ranges
-//                [W_hi X_hi | W_hi X_lo | W_lo X_hi] that the epilogue adds in fp32 (2 MMAs per K16 block instead of 3)
+//   precision  = fp16 hi/lo split, the same three products as rollout_tc.cu, kept in two accumulator column ranges
+//                [W_hi X_hi + W_lo X_hi | W_hi X_lo] that the epilogue adds in fp32 (2 MMAs per K16 block instead of 3)
 //
 // Measured on B200 (tools/tc_rate.py): a kind::f16 MMA with M = 128 costs max(N / 2, 32 + N / 4) cycles -- below N = 128
 // the 4 KB A fetch from shared memory (128 B/clk) sets the pace, not the tensor pipe; and it needs a lean issue loop (one
@@ -22,14 +22,15 @@
 // separately and ~300 with per-MMA index arithmetic).
 //
 // Warp roles (576 threads): warp 0 streams the member's weight image from L2 through a shared-memory ring (1-D bulk
-// async copies, one stage = up to `kps` K16 blocks of one M tile, hi + lo); warp 1 = one elected thread walking a
-// per-step stage table (built once in shared memory) and issuing the MMAs; warps 2-9 are the epilogue of M tile 0,
-// warps 10-17 of M tile 1 (quarter = TMEM lane quarter, two column slices each).  The layer input is double-buffered, so
-// tile 0's epilogue stores while tile 1's MMAs still read the previous buffer, and the next layer's first 8 K blocks
-// (produced by tile 0) are issued straight behind tile 1's MMAs while tile 1's epilogue runs: the tensor pipe does not
-// drain between the layers of one dependent chain.
-// Everything else (prologue gather / normalise / reward, bounded logvar, Gaussian sample, obs_postproc --
-// cadm/dynamics/core/utils.py:141-168) matches rollout_tc.cu, re-indexed for rows-as-columns.
+// async copies, one stage = up to `kps` K16 blocks of one M tile, hi + lo); warp 1 = one elected thread issuing the MMAs
+// from a compile-time schedule (reference architecture) or a per-step stage table; warps 2-17 are the epilogue: all 16
+// take M tile 0 and then M tile 1 (quarter = TMEM lane quarter, four column slices).  The layer input is double-buffered,
+// so tile 0's epilogue stores while tile 1's MMAs still read the previous buffer, and the next layer's first 8 K blocks
+// (produced by tile 0) are issued straight behind tile 1's MMAs while tile 1's epilogue runs.
+// The per-step serial part is kept short: the step's Gaussian draws and the next step's action prefetch run while the
+// warps wait for layer 1; the final epilogue (bounded logvar, sample, obs_postproc -- cadm/dynamics/core/utils.py:141-168)
+// is one thread per (row, state dim) and writes the next step's state features straight into the layer-0 operand, the
+// warps without head outputs build its action / context features meanwhile; the reward reads the CURRENT state (quirk Q4).
 #include <algorithm>
 
 #include "common.cuh"
