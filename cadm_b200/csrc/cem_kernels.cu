@@ -182,8 +182,9 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
         keys[i] = key;
     }
     __syncthreads();
-    if (n <= (int)blockDim.x && !R.mode_rs) {
-        // rank by counting: keys are distinct (the index is part of the key), so rank = #smaller keys
+    if (n <= 256 && !R.mode_rs) {
+        // rank by counting: keys are distinct (the index is part of the key), so rank = #smaller keys.  O(n^2 / 32) broadcast
+        // loads: 1.4k for n = 200, but 20k (10 us) for n = 800 -- above 256 candidates the bitonic sort below is faster
         if (tid < n) {
             const unsigned long long mine = keys[tid];
             int rank = 0;
@@ -215,23 +216,28 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
     for (int i = tid; i < K; i += blockDim.x)
         if (R.elites_log) R.elites_log[(size_t)mi * K + i] = s_el[i];
     if (R.stage_elites) {
-        // gather the elite sequences with independent, coalesced loads (4 in flight per thread), then reduce from shared
-        // memory
-        const int total = K * hA;
-        for (int i0 = tid; i0 < total; i0 += 4 * blockDim.x) {
-            float v[4];
+        // gather the elite sequences, one work item = (elite, block of 4 coordinates): a local elite is copied from this rank's
+        // actions; an elite owned by another rank is regenerated from the counter-based stream with ONE Philox call per block
+        // (the arithmetic of sample_actions_kernel, so every rank holds the same bits), then reduce from shared memory
+        const int nb = (hA + 3) >> 2;
+        for (int i = tid; i < K * nb; i += blockDim.x) {
+            const int jx = i / nb, b = i - jx * nb;
+            const int ni = s_el[jx];
+            const bool local = ni >= R.n_offset && ni < R.n_offset + R.n_local;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (!local && !R.z) w = philox(R.seed, (uint32_t)b, (uint32_t)ni, (uint32_t)mi, ((uint32_t)R.it << 8) | kStreamZ);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * blockDim.x;
-                if (i < total) {
-                    const int jx = i / hA, k = i - jx * hA;
-                    v[u] = elite_action(R, mi, s_el[jx], k, hA, R.mean[(size_t)mi * hA + k], R.var[(size_t)mi * hA + k]);
+            for (int l = 0; l < 4; ++l) {
+                const int k = 4 * b + l;
+                if (k >= hA) break;
+                float v;
+                if (local) {
+                    v = R.actions[((size_t)mi * R.n_local + (ni - R.n_offset)) * hA + k];
+                } else {
+                    const float z = R.z ? R.z[((size_t)mi * R.n_global + ni) * hA + k] : trunc_normal(word_of(w, l));
+                    v = cem_action_value(R.mean[(size_t)mi * hA + k], R.var[(size_t)mi * hA + k], z);
                 }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * blockDim.x;
-                if (i < total) el[i] = v[u];
+                el[jx * hA + k] = v;
             }
         }
         __syncthreads();
