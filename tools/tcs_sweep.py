@@ -44,4 +44,6 @@ def run(variant, rows, kps, trace=False, skew=0):
     model.engine.close()
 
 
-run(2, 32, 4, trace=True)
+run(1, 0, 4)
+for rows in (32, 48, 64):
+    run(2, rows, 4, trace=(rows == 32))
