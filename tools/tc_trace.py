@@ -1,4 +1,5 @@
-"""Print the clock64 phase trace of the tensor-core rollout kernel (CTA 0) for the C2 workload."""
+"""Print the clock64 phase trace of the 128-row-tile tensor-core rollout kernel (rollout_tc.cu, CTA 0) for the C2 workload
+(run with CADM_TC_VARIANT=1; tools/tcs_sweep.py traces the swapped-operand kernel)."""
 import sys
 import numpy as np
 import torch
@@ -23,4 +24,4 @@ for t in (1, 2, 15):
     print(f"step {t}: total {tr[t + 1, 0] - base if t + 1 < 30 else -1} cycles")
     print("  epi :", " ".join(f"{n}={tr[t, i] - base}" for i, n in enumerate(names)))
     print("  pro : prefetch=%d reward=%d built=%d" % (tr[t, 13] - base, tr[t, 14] - base, tr[t, 15] - base))
-    print("  mma :", " ".join(f"g{g}:first_ready={tr[t, 32 + 4 * g] - base},issued={tr[t, 33 + 4 * g] - base},xwait={tr[t, 34 + 4 * g]},wwait={tr[t, 35 + 4 * g]},issue={tr[t, 56 + g]}" for g in range(5)))
+    print("  mma :", " ".join(f"g{g}:first_ready={tr[t, 32 + 4 * g] - base},issued={tr[t, 33 + 4 * g] - base}" for g in range(5)))
