@@ -155,8 +155,9 @@ class PlannerModelBase:
         self._push_norm()
 
     def fit(self, *args, **kwargs):
-        raise NotImplementedError("training (fit) is outside the planner hot path this engine replaces; "
-                                  "train with the reference and load() the checkpoint")
+        raise NotImplementedError("fit() is provided for the PE-TS / vanilla model (mlp_ensemble_cem_dynamics.py); for the CaDM "
+                                  "model (context encoder, backward model, multi-step future loss) train with the reference "
+                                  "and load() the checkpoint")
 
     # ------------------------------------------------------------------ planning
     def _next_seed(self):

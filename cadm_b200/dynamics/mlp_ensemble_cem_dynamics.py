@@ -34,6 +34,16 @@ class MLPEnsembleCEMDynamicsModel(PlannerModelBase):
         (next_obs, mu, logvar) as NumPy; mu / logvar are the outputs of the reference's `_get_pred` (:185-189)."""
         return tuple(t.cpu().numpy() for t in self.engine.predict(obs, act, None, eps, seed))
 
+    def fit(self, obs, act, obs_next, epochs=1000, compute_normalization=True, valid_split_ratio=None,
+            rolling_average_persitency=None, verbose=False, log_tabular=False, max_logging=5000, rng=None):
+        """mlp_ensemble_cem_dynamics.py:209-323.  Training is not the hot path this package accelerates: it runs the
+        reference's loss and loop through PyTorch autograd on the engine's device (cadm_b200/dynamics/training.py), then
+        repacks the weights for the planner.  Returns a small dict (epochs run, last training losses)."""
+        from .training import fit_ensemble
+        return fit_ensemble(self, np.asarray(obs), np.asarray(act), np.asarray(obs_next), epochs=epochs,
+                            valid_split_ratio=valid_split_ratio, rolling_average_persitency=rolling_average_persitency,
+                            verbose=verbose, max_logging=max_logging, rng=rng)
+
     def compute_normalization(self, obs, act, delta):
         """mlp_ensemble_cem_dynamics.py:344-352."""
         assert obs.shape[0] == delta.shape[0] == act.shape[0]

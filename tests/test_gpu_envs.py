@@ -246,3 +246,35 @@ def test_other_architectures(hidden, precision, variant, monkeypatch):
     pr, st = model.engine.rollout(obs, actions, None, eps, trace=True)
     assert rel_err(st.cpu().numpy(), o_st, axis=(1, 2, 3)) < TOL
     assert np.max(np.abs(pr.cpu().numpy() - o_ret)) / np.max(np.abs(o_ret)) < TOL
+
+
+def test_fit_then_plan():
+    """fit() (PyTorch autograd on the device, cadm_b200/dynamics/training.py) hands its weights to the engine: after training on
+    synthetic transitions the hand-written kernels reproduce the trainer's own forward pass, the model has learned the
+    dynamics, and planning runs on the new weights."""
+    from cadm_b200.dynamics.training import EnsembleNLLTrainer
+    model, env = _pets("halfcheetah", "tc3x", n=64, h=8, E=5, p=10)
+    rng = np.random.default_rng(0)
+    D, A, N = env.obs_dim, env.act_dim, 2000
+    obs = rng.standard_normal((N, D)) * 0.5
+    act = rng.uniform(-1, 1, (N, A))
+    M = rng.standard_normal((D + A, D)) * 0.05
+    nxt = obs + np.concatenate([obs, act], axis=1) @ M
+    nxt[:, 0] = (np.concatenate([obs, act], axis=1) @ M)[:, 0]        # HalfCheetah postproc: o[0] is predicted directly
+    info = model.fit(obs, act, nxt, epochs=80, rng=np.random.default_rng(1))
+    assert info["epochs"] >= 1
+    stats = model.get_normalization_stats()[:6]
+    tr = EnsembleNLLTrainer(model._dyn, "halfcheetah", False, model.weight_decays, 0.0, 1e-3, device="cuda")
+    E, B = 5, 64
+    bo = np.tile(obs[None, :B], (E, 1, 1)).astype(np.float32)
+    ba = np.tile(act[None, :B], (E, 1, 1)).astype(np.float32)
+    with torch.no_grad():
+        mu_t, lv_t = tr.forward(torch.from_numpy(bo).cuda(), torch.from_numpy(ba).cuda(), tr._norm(stats))
+    nxt_k, mu_k, lv_k = model.predict(bo, ba, eps=np.zeros((E, B, D), np.float32))
+    assert rel_err(mu_k, mu_t.cpu().numpy()) < 1e-4 and rel_err(lv_k, lv_t.cpu().numpy()) < 1e-4
+    # the trained model predicts the synthetic dynamics far better than chance (targets have unit variance after normalisation)
+    delta = env.targ_proc(obs[:B], nxt[:B])
+    pred = mu_k[0] * (stats[5] + 1e-10) + stats[4]
+    assert np.mean((pred - delta) ** 2) < 0.5 * np.mean((delta - delta.mean(0)) ** 2)
+    plan = model.get_action(obs[:2].astype(np.float32), np.zeros((2, 8, A), np.float32), np.full((2, 8, A), 0.25, np.float32))
+    assert plan.shape == (2, 8, A) and np.isfinite(plan).all()
