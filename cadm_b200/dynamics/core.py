@@ -3,8 +3,8 @@
 The reference builds its whole TF graph in the constructor (mlp_ensemble_cem_dynamics.py:29-189,
 mlp_cadm_ensemble_cem_dynamics.py:26-342); here the constructor allocates the variables (NumPy, reference
 initialisation) and a PlannerEngine.  Only the planning surface is implemented:
-get_action / get_context_pred / get_normalization_stats / save / load, plus the additive predict().
-`fit()` (training) is out of scope and raises.
+get_action / get_context_pred / get_normalization_stats / save / load, plus the additive predict().  `fit()` is the
+widening row of SURVEY.md section 8(f): it lives in training.py (PyTorch autograd) and hands the arrays back here.
 """
 from collections import OrderedDict
 
@@ -77,6 +77,7 @@ class PlannerModelBase:
         rng = np.random.default_rng(seed)
         E, H = ensemble_size, hidden_sizes[0]
         self._enc = None
+        self._back = None                                            # backward model, only built when back_coeff > 0
         if self._has_context:
             sizes = [(D + A) * history_length] + list(self.cp_hidden_sizes) + [context_out_dim]
             self._enc = dict(
@@ -84,12 +85,10 @@ class PlannerModelBase:
                 b=[np.zeros((E, 1, sizes[i + 1]), np.float32) for i in range(len(sizes) - 1)])
         In = P + A + self.context_out_dim
         sizes = [In] + list(hidden_sizes)
-        self._dyn = dict(
-            W=[_trunc_normal(rng, (E, sizes[i], sizes[i + 1]), 1 / (2 * np.sqrt(sizes[i]))) for i in range(len(hidden_sizes))],
-            b=[np.zeros((E, 1, sizes[i + 1]), np.float32) for i in range(len(hidden_sizes))],
-            W_mu=_trunc_normal(rng, (E, H, D), 1 / (2 * np.sqrt(H))), b_mu=np.zeros((E, 1, D), np.float32),
-            W_lv=_trunc_normal(rng, (E, H, D), 1 / (2 * np.sqrt(H))), b_lv=np.zeros((E, 1, D), np.float32),
-            max_logvar=np.ones((1, D), np.float32) / 2.0, min_logvar=-np.ones((1, D), np.float32) * 10.0)
+        self._dyn = self._new_mlp(rng, E, sizes, D)
+        if self._has_context and getattr(self, "back_coeff", 0.0) > 0.0:
+            # 'backward_model' scope (mlp_cadm_ensemble_cem_dynamics.py:212-264): same shapes, created after the forward model
+            self._back = self._new_mlp(rng, E, sizes, D)
 
         cfg = PlannerConfig(env=self.env_name, obs_dim=D, proc_obs_dim=P, act_dim=A, ctx_dim=self.context_out_dim,
                             hist_len=history_length, hidden=H, n_hidden=len(hidden_sizes),
@@ -102,6 +101,18 @@ class PlannerModelBase:
         self._push_params()
         self._push_norm()
 
+    @staticmethod
+    def _new_mlp(rng, E, sizes, D):
+        """Variables of one create_*_ensemble_cem_mlp call (core/utils.py:306-336): hidden layers, mu / logvar heads,
+        max / min logvar."""
+        H, n = sizes[-1], len(sizes) - 1
+        return dict(
+            W=[_trunc_normal(rng, (E, sizes[i], sizes[i + 1]), 1 / (2 * np.sqrt(sizes[i]))) for i in range(n)],
+            b=[np.zeros((E, 1, sizes[i + 1]), np.float32) for i in range(n)],
+            W_mu=_trunc_normal(rng, (E, H, D), 1 / (2 * np.sqrt(H))), b_mu=np.zeros((E, 1, D), np.float32),
+            W_lv=_trunc_normal(rng, (E, H, D), 1 / (2 * np.sqrt(H))), b_lv=np.zeros((E, 1, D), np.float32),
+            max_logvar=np.ones((1, D), np.float32) / 2.0, min_logvar=-np.ones((1, D), np.float32) * 10.0)
+
     # ------------------------------------------------------------------ parameters
     @property
     def params(self):
@@ -110,10 +121,12 @@ class PlannerModelBase:
         if self._enc is not None:
             for W, b in zip(self._enc["W"], self._enc["b"]):
                 out += [W, b]
-        d = self._dyn
-        for W, b in zip(d["W"], d["b"]):
-            out += [W, b]
-        out += [d["W_mu"], d["b_mu"], d["W_lv"], d["b_lv"], d["max_logvar"], d["min_logvar"]]
+        for d in (self._dyn, self._back):
+            if d is None:
+                continue
+            for W, b in zip(d["W"], d["b"]):
+                out += [W, b]
+            out += [d["W_mu"], d["b_mu"], d["W_lv"], d["b_lv"], d["max_logvar"], d["min_logvar"]]
         return out
 
     def set_params(self, arrays):
@@ -121,7 +134,7 @@ class PlannerModelBase:
         cur = self.params
         if len(arrays) < len(cur):
             raise ValueError(f"expected at least {len(cur)} arrays, got {len(arrays)}")
-        for i, (dst, src) in enumerate(zip(cur, arrays)):       # extra arrays (backward model) are ignored
+        for i, (dst, src) in enumerate(zip(cur, arrays)):       # extra arrays (a backward model this one lacks) are ignored
             if dst.shape != src.shape:
                 raise ValueError(f"variable {i}: shape {src.shape} does not match {dst.shape}")
             dst[...] = src
@@ -153,11 +166,6 @@ class PlannerModelBase:
         if self.normalize_input:
             self.normalization = joblib.load(load_path + "_norm_stats")
         self._push_norm()
-
-    def fit(self, *args, **kwargs):
-        raise NotImplementedError("fit() is provided for the PE-TS / vanilla model (mlp_ensemble_cem_dynamics.py); for the CaDM "
-                                  "model (context encoder, backward model, multi-step future loss) train with the reference "
-                                  "and load() the checkpoint")
 
     # ------------------------------------------------------------------ planning
     def _next_seed(self):

@@ -2,8 +2,9 @@
 
 Mirror of cadm/dynamics/mlp_cadm_ensemble_cem_dynamics.py (class MLPEnsembleCEMDynamicsModel, :12): same
 constructor keywords, same get_action / get_context_pred / get_normalization_stats / save / load behaviour.
-The backward-dynamics model and the multi-step future loss exist only for training (:212-264) and are not built;
-load() ignores their variables if a checkpoint holds them (they come last in the variable list).
+The backward-dynamics model exists only for training (:212-264): its variables are created when back_coeff > 0 (after the
+forward model's, as in the reference's variable list), trained by fit() and saved; the planner never reads them.  A model
+built with back_coeff = 0 ignores them when load() finds them at the tail of a checkpoint.
 """
 from collections import OrderedDict
 
@@ -53,6 +54,19 @@ class MLPEnsembleCEMDynamicsModel(PlannerModelBase):
         if ctx is None:
             ctx = self.engine.encode_context(np.asarray(cp_obs, np.float32), np.asarray(cp_act, np.float32))
         return tuple(t.cpu().numpy() for t in self.engine.predict(obs, act, ctx, eps, seed))
+
+    def fit(self, obs, act, obs_next, cp_obs, cp_act, future_bool, epochs=1000, compute_normalization=True,
+            valid_split_ratio=None, rolling_average_persitency=None, verbose=False, log_tabular=False, max_logging=5000,
+            rng=None):
+        """mlp_cadm_ensemble_cem_dynamics.py:382-569: obs / act / obs_next carry future_length steps per sample
+        ([n, dim*future_length]), cp_obs / cp_act the history, future_bool [n, future_length] masks steps past the end
+        of a path.  Runs the reference's loss and loop through PyTorch autograd on the engine's device
+        (cadm_b200/dynamics/training.py), then repacks encoder and forward model for the planner."""
+        from .training import fit_cadm_ensemble
+        return fit_cadm_ensemble(self, np.asarray(obs), np.asarray(act), np.asarray(obs_next), np.asarray(cp_obs),
+                                 np.asarray(cp_act), np.asarray(future_bool), epochs=epochs,
+                                 valid_split_ratio=valid_split_ratio, rolling_average_persitency=rolling_average_persitency,
+                                 verbose=verbose, max_logging=max_logging, rng=rng)
 
     def compute_normalization(self, obs, act, delta, cp_obs, cp_act, back_delta):
         """mlp_cadm_ensemble_cem_dynamics.py:590-602."""
