@@ -1,0 +1,107 @@
+"""Generate tests/golden/sampler_golden.npz by running the UNMODIFIED reference sampler and sample processor.
+
+`cadm/samplers/sampler.py` (Sampler.obtain_samples) and `cadm/samplers/model_sample_processor.py`
+(ModelSampleProcessor.process_samples) are pure NumPy at run time; only their import chain pulls in TensorFlow 1.15 and
+pyprind, which this container lacks.  Both are replaced by inert stand-ins in sys.modules (no reference file is modified
+or copied), the reference classes are imported from /root/reference and driven with the stand-in environment and policy
+of tests/sampler_fakes.py.  Recorded per scenario: every argument of every policy.get_actions() call, the finished paths,
+and the arrays process_samples() returns.  tests/test_samplers.py replays the same scenarios through cadm_b200's classes.
+
+Run in the build container (needs /root/reference):  python tests/golden/make_sampler_golden.py
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+sys.dont_write_bytecode = True                              # /root/reference is read-only: leave no __pycache__ there
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from sampler_fakes import FakeEnv, ScriptedPolicy          # noqa: E402
+
+SCENARIOS = dict(
+    # name: (context, state_diff, use_cem, history_length, future_length, num_rollouts, max_path_length, horizon)
+    cem_ctx_diff=(True, True, True, 3, 4, 3, 12, 5),
+    cem_ctx_abs=(True, False, True, 3, 4, 3, 12, 5),
+    cem_plain=(False, False, True, 1, 1, 3, 12, 5),
+    rs_ctx=(True, True, False, 4, 2, 2, 10, 5),
+)
+
+
+class _Inert(types.ModuleType):
+    """Stands in for a module the reference imports but never touches on this path."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Inert(self.__name__ + "." + name)
+
+    def __call__(self, *a, **k):
+        return self
+
+
+class _ProgBar:
+    def __init__(self, *a, **k):
+        pass
+
+    def update(self, *a, **k):
+        pass
+
+    def stop(self):
+        pass
+
+
+def import_reference():
+    sys.modules.setdefault("tensorflow", _Inert("tensorflow"))
+    pp = types.ModuleType("pyprind")
+    pp.ProgBar = _ProgBar
+    sys.modules.setdefault("pyprind", pp)
+    sys.path.insert(0, "/root/reference")
+    from cadm.samplers.model_sample_processor import ModelSampleProcessor
+    from cadm.samplers.sampler import Sampler
+    return Sampler, ModelSampleProcessor
+
+
+def run(Sampler, Processor, name):
+    context, state_diff, use_cem, K, F, m, T, h = SCENARIOS[name]
+    FakeEnv._copies = 0
+    env = FakeEnv()
+    policy = ScriptedPolicy(h, env.act_dim, use_cem)
+    sampler = Sampler(env=env, policy=policy, num_rollouts=m, max_path_length=T, n_parallel=1, use_cem=use_cem, horizon=h,
+                      context=context, state_diff=state_diff, history_length=K)
+    paths = sampler.obtain_samples(log=False)
+    out = {"n_calls": np.int64(len(policy.calls)), "n_paths": np.int64(len(paths))}
+    for i, c in enumerate(policy.calls):
+        for k, v in c.items():
+            out[f"call{i}_{k}"] = v
+    for i, p in enumerate(paths):
+        for k in ("observations", "actions", "rewards", "dones", "cp_obs", "cp_act"):
+            out[f"path{i}_{k}"] = np.array(p[k], copy=True)
+        out[f"path{i}_env_t"] = p["env_infos"]["t"]
+    if use_cem:
+        out["final_prev_sol"] = sampler.prev_sol.copy()
+    samples = Processor(discount=0.99, max_path_length=T, context=context, future_length=F).process_samples(paths, log=False)
+    for k, v in samples.items():
+        out[f"samples_{k}"] = v
+    for i, p in enumerate(paths):                           # process_samples pads short paths in place
+        out[f"path{i}_len_after"] = np.int64(p["observations"].shape[0])
+        out[f"path{i}_returns"] = p["returns"]
+    return out
+
+
+def main():
+    Sampler, Processor = import_reference()
+    blob = {}
+    for name in SCENARIOS:
+        for k, v in run(Sampler, Processor, name).items():
+            blob[f"{name}/{k}"] = v
+    path = os.path.join(HERE, "sampler_golden.npz")
+    np.savez_compressed(path, **blob)
+    print(path, len(blob), "arrays", os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
