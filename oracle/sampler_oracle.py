@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY: loop restatement of the future-window construction of
 cadm/samplers/model_sample_processor.py:60-92, to check cadm_b200.samplers.ModelSampleProcessor at sizes and shapes the
-recorded reference scenarios (tests/golden/sampler_golden.npz, produced by the unmodified reference) do not cover.
+recorded reference scenarios (tests/golden/recorded/sampler_golden.npz, produced by the unmodified reference) do not cover.
 Pinned by those scenarios in tests/test_samplers.py."""
 import numpy as np
 

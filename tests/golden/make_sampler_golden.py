@@ -1,4 +1,4 @@
-"""Generate tests/golden/sampler_golden.npz by running the UNMODIFIED reference sampler and sample processor.
+"""Generate tests/golden/recorded/sampler_golden.npz by running the UNMODIFIED reference sampler and sample processor.
 
 `cadm/samplers/sampler.py` (Sampler.obtain_samples) and `cadm/samplers/model_sample_processor.py`
 (ModelSampleProcessor.process_samples) are pure NumPy at run time; only their import chain pulls in TensorFlow 1.15 and
@@ -98,7 +98,7 @@ def main():
     for name in SCENARIOS:
         for k, v in run(Sampler, Processor, name).items():
             blob[f"{name}/{k}"] = v
-    path = os.path.join(HERE, "sampler_golden.npz")
+    path = os.path.join(HERE, "recorded", "sampler_golden.npz")
     np.savez_compressed(path, **blob)
     print(path, len(blob), "arrays", os.path.getsize(path), "bytes")
 

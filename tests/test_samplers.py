@@ -1,5 +1,5 @@
 """Host-side sampler loop and sample processor (cadm_b200/samplers.py) against scenarios recorded from the UNMODIFIED
-reference classes (tests/golden/sampler_golden.npz, generator tests/golden/make_sampler_golden.py): every argument of every
+reference classes (tests/golden/recorded/sampler_golden.npz, generator tests/golden/make_sampler_golden.py): every argument of every
 policy.get_actions() call, every finished path and every array of process_samples() must agree bit for bit.  CPU only."""
 import os
 import sys
@@ -13,7 +13,7 @@ from sampler_fakes import FakeEnv, ScriptedPolicy
 from cadm_b200.samplers import HostPlannerState, IterativeEnvExecutor, ModelSampleProcessor, Sampler, discount_cumsum
 from oracle.sampler_oracle import future_windows_loops
 
-GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sampler_golden.npz"))
+GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "recorded", "sampler_golden.npz"))
 SCENARIOS = dict(                      # the generator's table
     cem_ctx_diff=(True, True, True, 3, 4, 3, 12, 5),
     cem_ctx_abs=(True, False, True, 3, 4, 3, 12, 5),
