@@ -21,8 +21,8 @@ class FakeEnv:
     """obs' = 0.9 obs + B act + drift(k); episode j of copy k ends (done=True) after `lengths[k][j]` steps."""
     _copies = 0
 
-    def __init__(self, obs_dim=3, act_dim=2, lengths=((5, 2, 30), (30, 7), (9, 30, 30))):
-        self.obs_dim, self.act_dim = obs_dim, act_dim
+    def __init__(self, obs_dim=3, act_dim=2, lengths=((5, 2, 30), (30, 7), (9, 30, 30)), round32=False):
+        self.obs_dim, self.act_dim, self.round32 = obs_dim, act_dim, round32
         self.observation_space, self.action_space = _Box(obs_dim), _Box(act_dim)
         self.lengths = lengths
         self.k, self.episode, self.t = 0, -1, 0
@@ -31,7 +31,7 @@ class FakeEnv:
 
     def __deepcopy__(self, memo):
         # the executors clone the environment once per rollout slot; every clone gets its own index
-        new = FakeEnv(self.obs_dim, self.act_dim, self.lengths)
+        new = FakeEnv(self.obs_dim, self.act_dim, self.lengths, self.round32)
         new.k = FakeEnv._copies % len(self.lengths)
         FakeEnv._copies += 1
         return new
@@ -39,12 +39,16 @@ class FakeEnv:
     def reset(self):
         self.episode += 1
         self.t = 0
-        self.obs = np.sin(np.arange(self.obs_dim) + 1.0 + 3.0 * self.k + 0.5 * self.episode)
+        self.obs = self._q(np.sin(np.arange(self.obs_dim) + 1.0 + 3.0 * self.k + 0.5 * self.episode))
         return self.obs.copy()
+
+    def _q(self, x):
+        # round32: observations that float32 represents exactly (what a float32 simulator hands out)
+        return x.astype(np.float32).astype(np.float64) if self.round32 else x
 
     def step(self, action):
         action = np.asarray(action, dtype=np.float64)
-        self.obs = 0.9 * self.obs + action @ self.B + 0.01 * (self.k + 1)
+        self.obs = self._q(0.9 * self.obs + action @ self.B + 0.01 * (self.k + 1))
         self.t += 1
         plan = self.lengths[self.k]
         done = self.t >= plan[min(self.episode, len(plan) - 1)]
