@@ -404,7 +404,8 @@ __global__ void session_observe_kernel(const float* __restrict__ obs, const floa
         const int slot = cnt < K ? cnt : K - 1;
         for (int d = tid; d < D; d += blockDim.x) {
             const float o = obs[(size_t)mi * D + d];
-            ho[slot * D + d] = state_diff ? next_obs[(size_t)mi * D + d] - o : o;
+            const float nx = next_obs[(size_t)mi * D + d];
+            ho[slot * D + d] = state_diff == 2 ? nx : (state_diff ? nx - o : o);
         }
         for (int a = tid; a < A; a += blockDim.x) ha[slot * A + a] = action[(size_t)mi * A + a];
         if (tid == 0) counts[mi] = cnt + 1;

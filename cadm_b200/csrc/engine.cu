@@ -734,7 +734,7 @@ int cadm_session_observe(void* handle, int32_t m, const float* next_obs_host, co
     Engine* E = H(handle);
     if (!E) return CADM_ERR_ARG;
     const CadmConfig& c = E->cfg;
-    if (m < 1 || m > c.m_max || !next_obs_host) return fail(E, CADM_ERR_ARG, "bad arguments");
+    if (m < 1 || m > c.m_max || !next_obs_host || state_diff < 0 || state_diff > 2) return fail(E, CADM_ERR_ARG, "bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
     const int K = c.ctx_dim > 0 ? c.hist_len : 1;
     CU(E, cudaMemcpyAsync(E->s_next, next_obs_host, (size_t)m * c.obs_dim * sizeof(float), cudaMemcpyHostToDevice, s));

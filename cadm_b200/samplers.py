@@ -83,12 +83,15 @@ class PlannerSession:
                                           C.c_void_p(self._act.data_ptr()), self._stream()))
         return self._act.numpy().reshape(self.m, self.act_dim).copy()
 
-    def observe(self, next_obses, dones=None):
-        """Append the transition to the history buffers and reset finished episodes (sampler.py:164-195); asynchronous."""
+    def observe(self, next_obses, dones=None, entry=None):
+        """Append the transition to the history buffers and reset finished episodes (sampler.py:164-195); asynchronous.
+        The history entry is the observation acted on, or next_obs - obs with state_diff, formed on the device from the
+        float32 copies.  A host that holds float64 observations and wants the reference's rounding of the difference
+        (subtract in float64, then round) passes it as `entry` [m, D]; it is stored as is."""
         e = self.engine
-        nxt = np.asarray(next_obses, dtype=np.float32)
+        nxt = np.asarray(next_obses if entry is None else entry, dtype=np.float32)
         if nxt.shape != (self.m, self.obs_dim):
-            raise ValueError(f"next_obses must be [{self.m}, {self.obs_dim}], got {nxt.shape}")
+            raise ValueError(f"next_obses / entry must be [{self.m}, {self.obs_dim}], got {nxt.shape}")
         with torch.cuda.device(e.device):
             torch.cuda.current_stream(e.device).synchronize()          # the previous observe() may still read the staging buffers
             self._next.numpy()[...] = nxt.reshape(-1)
@@ -96,8 +99,8 @@ class PlannerSession:
             if dones is not None:
                 self._mask.numpy()[...] = np.asarray(dones, dtype=bool).astype(np.uint8)
                 done_p = C.c_void_p(self._mask.data_ptr())
-            e._chk(e.lib.cadm_session_observe(e._h, self.m, C.c_void_p(self._next.data_ptr()), done_p, int(self.state_diff),
-                                              self._stream()))
+            mode = 2 if entry is not None else int(self.state_diff)
+            e._chk(e.lib.cadm_session_observe(e._h, self.m, C.c_void_p(self._next.data_ptr()), done_p, mode, self._stream()))
 
     def state(self):
         """Host copies of (prev_sol [m, h, A], history_state [m, D*K], history_act [m, A*K], state_counts [m])."""
@@ -163,6 +166,7 @@ class HostPlannerState:
         dones = np.asarray(dones, dtype=bool)
         self.counts += 1
         self.reset_history(dones)
+        return entry
 
 
 class IterativeEnvExecutor:
@@ -307,9 +311,9 @@ class Sampler:
                 rec["agent_infos"].append(agent_infos[i])
                 rec["cp_obs"].append(st.history_state[i].copy())
                 rec["cp_act"].append(st.history_act[i].copy())
-            st.observe(obs_now, acts, obs_next, dones)
+            entry = st.observe(obs_now, acts, obs_next, dones)
             if self.session is not None:
-                self.session.observe(obs_next, dones)
+                self.session.observe(obs_next, dones, entry=entry)       # the float64 difference, rounded once
             for i in np.flatnonzero(dones):
                 rec = running[i]
                 paths.append(dict(

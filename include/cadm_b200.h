@@ -190,7 +190,9 @@ int cadm_plan_cem_host(void* handle, int32_t m, const float* obs_host, const flo
  * the environment step, by  cadm_session_observe (H2D of next_obs [m, D] and done [m]; asynchronous).  world == 1. */
 int cadm_session_reset(void* handle, int32_t m, const uint8_t* mask_host /* [m] or NULL = all */, void* stream);
 int cadm_session_act(void* handle, int32_t m, const float* obs_host, uint64_t seed, float* action_host, void* stream);
-/* history entry = next_obs - obs when state_diff != 0 (run_cadm_pets.py:137 default), else obs (sampler.py:166-177) */
+/* history entry: state_diff == 0: obs (sampler.py:166-177); 1: next_obs - obs, subtracted in fp32 (run_cadm_pets.py:137
+ * default); 2: `next_obs_host` holds the entry itself -- for a host whose environments hand out float64 observations and
+ * that wants the reference's rounding, float32(next_obs - obs) with the subtraction in float64 */
 int cadm_session_observe(void* handle, int32_t m, const float* next_obs_host, const uint8_t* done_host, int32_t state_diff,
                          void* stream);
 /* copies of the state for inspection (any pointer may be NULL): prev_sol [m, h, A], history [m, D*K] / [m, A*K], counts [m] */

@@ -13,10 +13,12 @@ from helpers import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def test_sampler_with_device_session_records_the_same_paths_as_the_host_loop():
+@pytest.mark.parametrize("round32", [True, False])
+def test_sampler_with_device_session_records_the_same_paths_as_the_host_loop(round32):
     """cadm_b200.samplers.Sampler with device_state=True (PlannerSession: plans and histories stay on the GPU) against
     device_state=False (the reference's loop: NumPy state fed to policy.get_actions every step).  Same engine arithmetic,
-    same seeds, float32-representable observations: the recorded paths must agree bit for bit."""
+    same seeds: the recorded paths must agree bit for bit -- also with float64 observations that float32 cannot hold
+    exactly, because the Sampler hands the session the float64 state difference (cadm_session_observe, state_diff = 2)."""
     from sampler_fakes import FakeEnv
     from cadm_b200.policies.mpc_controller import MPCController
     from cadm_b200.samplers import Sampler
@@ -28,7 +30,7 @@ def test_sampler_with_device_session_records_the_same_paths_as_the_host_loop():
         policy = MPCController(name="policy", env=env, dynamics_model=model, use_cem=True, n_candidates=64, horizon=horizon,
                                num_rollouts=m, context=True)
         FakeEnv._copies = 0
-        fake = FakeEnv(obs_dim=env.obs_dim, act_dim=env.act_dim, lengths=((4, 30), (30,)), round32=True)
+        fake = FakeEnv(obs_dim=env.obs_dim, act_dim=env.act_dim, lengths=((4, 30), (30,)), round32=round32)
         s = Sampler(fake, policy, num_rollouts=m, max_path_length=13, use_cem=True, horizon=horizon, context=True,
                     state_diff=True, history_length=10, device_state=device_state)
         assert (s.session is not None) == device_state
