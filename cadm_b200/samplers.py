@@ -21,7 +21,8 @@ the actions equal the host-side loop's bit for bit.
 The callers and data formats either side of the planner live here too, as host code with the reference's
 interfaces: `Sampler` (sampler.py: the rollout loop that owns the state above and records paths -- it plans through a
 `PlannerSession` when the policy's dynamics model has an engine, and through `policy.get_actions` with NumPy state
-otherwise), `IterativeEnvExecutor` (vectorized_env_executor.py:7-69) and `ModelSampleProcessor`
+otherwise), `IterativeEnvExecutor` (vectorized_env_executor.py:7-69), `rollout_multi` / `context_rollout_multi`
+(samplers/utils.py: the trainer's evaluation rollouts, same state) and `ModelSampleProcessor`
 (model_sample_processor.py: paths -> the arrays `fit()` takes).  tests/test_samplers.py replays scenarios recorded from
 the unmodified reference classes (tests/golden/make_sampler_golden.py) through them and compares bit for bit.
 """
@@ -329,6 +330,68 @@ class Sampler:
         self.total_timesteps_sampled += self.total_samples
         self.last_timing = {log_prefix + "PolicyExecTime": policy_time, log_prefix + "EnvExecTime": env_time}
         return paths
+
+
+# ------------------------------------------------------------------------------------------------ evaluation rollouts
+
+def _evaluate(vec_env, policy, discrete, num_rollouts, test_total, state_diff, act_dim, use_cem, horizon, history_length,
+              with_context, device_state):
+    """Average undiscounted return of the first `test_total` episodes that finish (cadm/samplers/utils.py:5-41 and
+    :44-124; the trainer's test phase, mb_trainer.py:250-280).  Same planner state as Sampler.obtain_samples."""
+    m = vec_env.num_envs
+    obses = np.asarray(vec_env.reset())
+    K = history_length if with_context else 1
+    st = HostPlannerState(m, obses.shape[1], act_dim, K, bool(state_diff), use_cem, horizon)
+    model = getattr(policy, "dynamics_model", None)
+    has_engine = getattr(model, "engine", None) is not None
+    if device_state is None:
+        device_state = bool(use_cem and has_engine)
+    if device_state and not (use_cem and has_engine):
+        raise CadmError("device_state needs use_cem=True and a policy whose dynamics_model owns a PlannerEngine")
+    session = PlannerSession(model, m, state_diff=bool(state_diff)) if device_state else None
+    finished, running, n_test = [], np.zeros(m), 0
+    while n_test < test_total:
+        if session is not None:
+            actions = session.act(np.asarray(obses))
+        else:
+            kw = dict(cp_obs=st.history_state, cp_act=st.history_act) if with_context else {}
+            if use_cem:
+                sols, _ = policy.get_actions(obses, init_mean=st.prev_sol, init_var=st.init_var, **kw)
+                actions = st.shift(sols)
+            else:
+                actions, _ = policy.get_actions(obses, **kw)
+        if discrete:
+            actions = actions.reshape(-1)
+        next_obses, rewards, dones, _ = vec_env.step(actions)
+        running += np.asarray(rewards, dtype=np.float64).reshape(m)
+        if with_context or session is not None:
+            acts = np.eye(act_dim)[np.asarray(actions)] if discrete else np.asarray(actions).reshape(m, -1)
+            entry = st.observe(np.asarray(obses, dtype=np.float64), acts, np.asarray(next_obses, dtype=np.float64), dones)
+            if session is not None:
+                session.observe(np.asarray(next_obses), dones, entry=entry)
+        for i in np.flatnonzero(dones):
+            n_test += 1
+            finished.append(running[i])
+            running[i] = 0.
+            st.reset_plans(i)
+        obses = next_obses
+    return np.average(finished)
+
+
+def rollout_multi(vec_env, policy, discrete, animated=False, ignore_done=False, num_rollouts=10, test_total=20,
+                  adapt_batch_size=None, state_diff=False, act_dim=None, use_cem=False, horizon=None, context=None,
+                  history_length=None, device_state=None):
+    """cadm/samplers/utils.py:5-41 (models without a context encoder)."""
+    return _evaluate(vec_env, policy, discrete, num_rollouts, test_total, state_diff, act_dim, use_cem, horizon, history_length,
+                     False, device_state)
+
+
+def context_rollout_multi(vec_env, policy, discrete, animated=False, ignore_done=False, num_rollouts=10, test_total=20,
+                          adapt_batch_size=None, state_diff=False, act_dim=None, use_cem=False, horizon=None, context=None,
+                          history_length=None, device_state=None):
+    """cadm/samplers/utils.py:44-124 (the K-step history feeds the context encoder)."""
+    return _evaluate(vec_env, policy, discrete, num_rollouts, test_total, state_diff, act_dim, use_cem, horizon, history_length,
+                     True, device_state)
 
 
 # ------------------------------------------------------------------------------------------------ paths -> fit() arrays

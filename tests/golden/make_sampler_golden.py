@@ -5,7 +5,8 @@
 pyprind, which this container lacks.  Both are replaced by inert stand-ins in sys.modules (no reference file is modified
 or copied), the reference classes are imported from /root/reference and driven with the stand-in environment and policy
 of tests/sampler_fakes.py.  Recorded per scenario: every argument of every policy.get_actions() call, the finished paths,
-and the arrays process_samples() returns.  tests/test_samplers.py replays the same scenarios through cadm_b200's classes.
+and the arrays process_samples() returns; for the evaluation rollouts of `cadm/samplers/utils.py` (rollout_multi,
+context_rollout_multi) the calls and the returned average.  tests/test_samplers.py replays the same scenarios through cadm_b200's classes.
 
 Run in the build container (needs /root/reference):  python tests/golden/make_sampler_golden.py
 """
@@ -28,6 +29,14 @@ SCENARIOS = dict(
     cem_ctx_abs=(True, False, True, 3, 4, 3, 12, 5),
     cem_plain=(False, False, True, 1, 1, 3, 12, 5),
     rs_ctx=(True, True, False, 4, 2, 2, 10, 5),
+)
+
+
+EVAL_SCENARIOS = dict(
+    # name: (context, state_diff, use_cem, history_length, num_rollouts, max_path_length, horizon, test_total)
+    eval_plain_cem=(False, False, True, 1, 3, 12, 5, 5),
+    eval_ctx_cem_diff=(True, True, True, 3, 3, 12, 5, 5),
+    eval_ctx_rs_abs=(True, False, False, 4, 2, 10, 5, 4),
 )
 
 
@@ -65,6 +74,24 @@ def import_reference():
     return Sampler, ModelSampleProcessor
 
 
+def run_eval(name):
+    from cadm.samplers.utils import context_rollout_multi, rollout_multi
+    from cadm.samplers.vectorized_env_executor import IterativeEnvExecutor
+    context, state_diff, use_cem, K, m, T, h, total = EVAL_SCENARIOS[name]
+    FakeEnv._copies = 0
+    env = FakeEnv()
+    policy = ScriptedPolicy(h, env.act_dim, use_cem)
+    vec_env = IterativeEnvExecutor(env, m, T)
+    fn = context_rollout_multi if context else rollout_multi
+    avg = fn(vec_env, policy, False, num_rollouts=m, test_total=total, state_diff=state_diff, act_dim=env.act_dim,
+             use_cem=use_cem, horizon=h, context=context, history_length=K)
+    out = {"n_calls": np.int64(len(policy.calls)), "average": np.float64(avg)}
+    for i, c in enumerate(policy.calls):
+        for k, v in c.items():
+            out[f"call{i}_{k}"] = v
+    return out
+
+
 def run(Sampler, Processor, name):
     context, state_diff, use_cem, K, F, m, T, h = SCENARIOS[name]
     FakeEnv._copies = 0
@@ -97,6 +124,9 @@ def main():
     blob = {}
     for name in SCENARIOS:
         for k, v in run(Sampler, Processor, name).items():
+            blob[f"{name}/{k}"] = v
+    for name in EVAL_SCENARIOS:
+        for k, v in run_eval(name).items():
             blob[f"{name}/{k}"] = v
     path = os.path.join(HERE, "recorded", "sampler_golden.npz")
     np.savez_compressed(path, **blob)

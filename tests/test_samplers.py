@@ -10,7 +10,8 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from sampler_fakes import FakeEnv, ScriptedPolicy
 
-from cadm_b200.samplers import HostPlannerState, IterativeEnvExecutor, ModelSampleProcessor, Sampler, discount_cumsum
+from cadm_b200.samplers import (HostPlannerState, IterativeEnvExecutor, ModelSampleProcessor, Sampler, context_rollout_multi,
+                                discount_cumsum, rollout_multi)
 from oracle.sampler_oracle import future_windows_loops
 
 GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "recorded", "sampler_golden.npz"))
@@ -181,3 +182,29 @@ def test_paths_flow_from_the_sampler_through_the_processor_into_fit():
                              log=lambda *_: None)
     assert info["epochs"] >= 1 and np.isfinite(info["train_recon"]) and model.pushed == 1
     assert model._dataset["future_bool"].shape == data["concat_bool"].shape
+
+
+EVAL_SCENARIOS = dict(                 # the generator's table
+    eval_plain_cem=(False, False, True, 1, 3, 12, 5, 5),
+    eval_ctx_cem_diff=(True, True, True, 3, 3, 12, 5, 5),
+    eval_ctx_rs_abs=(True, False, False, 4, 2, 10, 5, 4),
+)
+
+
+@pytest.mark.parametrize("name", list(EVAL_SCENARIOS))
+def test_evaluation_rollouts_match_the_reference(name):
+    """rollout_multi / context_rollout_multi (cadm/samplers/utils.py): every policy call and the returned average."""
+    context, state_diff, use_cem, K, m, T, h, total = EVAL_SCENARIOS[name]
+    g = lambda k: GOLDEN[f"{name}/{k}"]
+    FakeEnv._copies = 0
+    env = FakeEnv()
+    policy = ScriptedPolicy(h, env.act_dim, use_cem)
+    fn = context_rollout_multi if context else rollout_multi
+    avg = fn(IterativeEnvExecutor(env, m, T), policy, False, num_rollouts=m, test_total=total, state_diff=state_diff,
+             act_dim=env.act_dim, use_cem=use_cem, horizon=h, context=context, history_length=K)
+    assert len(policy.calls) == int(g("n_calls"))
+    for i, call in enumerate(policy.calls):
+        assert set(call) == {k[len(f"{name}/call{i}_"):] for k in GOLDEN.files if k.startswith(f"{name}/call{i}_")}
+        for k, v in call.items():
+            _same(v, g(f"call{i}_{k}"), (i, k))
+    assert float(avg) == float(g("average"))
