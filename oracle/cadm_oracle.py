@@ -1,10 +1,16 @@
 """TEST INFRASTRUCTURE (oracle) -- CPU restatement of the CaDM CEM/MPC planner hot path.
 
-PARITY STATUS: "parity unpinned" by the reference itself -- /root/reference holds no tests, golden
+PARITY STATUS: pinned by the reference's own graph code.  /root/reference holds no tests, golden
 vectors or fixtures for this path (its only test is the failing stub cadm/__init__.py:1-9) and
-TensorFlow 1.15 cannot be imported or installed here, so the reference cannot be executed.  The pins
-are the hand-derived known-answer tests in tests/test_oracle_kat.py, which
-follow from the cited reference lines alone.
+TensorFlow 1.15 cannot be imported or installed here; but the planner is Python that composes ~35 TF
+functions, so tests/golden/make_reference_golden.py runs the UNMODIFIED builder functions of
+cadm/dynamics/core/utils.py and the unmodified environment classes over a NumPy stand-in for those
+functions (tests/golden/tf_numpy_shim.py), in float64, with the same weights and injected noise, and
+records what they compute (tests/golden/recorded/planner_reference*.npz).  tests/test_reference_pinned.py
+requires this oracle and the committed fixtures to reproduce those recordings (returns, elite indices,
+plans; CEM and random shooting; all six environments).  Not exercised by that: TensorFlow's kernels and
+random generators (noise is injected).  The hand-derived known-answer tests in tests/test_oracle_kat.py
+ remain as independent pins.
 
 Only `tests/`, `__graft_entry__.smoke()` and bench.py's `cpu_baseline` / `--impl reference` legs may
 import this package; the product (`cadm_b200/`) never does.

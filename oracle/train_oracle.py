@@ -3,8 +3,11 @@
 PE-TS: cadm/dynamics/core/utils.py:73-97 (forward on the bootstrap batch, soft-bounded logvar) and
 cadm/dynamics/mlp_ensemble_cem_dynamics.py:150-167 (mse / mu / var / reg / l2 losses).  CaDM: core/utils.py:605-622
 (encoder), :365-372 (input with the context appended), mlp_cadm_ensemble_cem_dynamics.py:266-314 (joint loss with the
-backward model) and :676-696 (flattening of the future_length-step samples, written here as explicit loops).  Parity unpinned by the reference
-(TensorFlow 1.15 cannot run here); pinned by closed-form cases and by finite differences in tests/test_training.py."""
+backward model) and :676-696 (flattening of the future_length-step samples, written here as explicit loops).  The forward passes (encoder,
+forward model with context, backward model, PE-TS model) of cadm_b200/dynamics/training.py are pinned by the reference's
+own builder functions run over the NumPy TensorFlow stand-in (tests/test_reference_pinned.py); the few lines that turn mu /
+logvar into the scalar losses live in the reference's model constructors, which cannot be run here: those are restated
+below and pinned by closed-form cases and finite differences in tests/test_training.py."""
 import numpy as np
 
 

@@ -1,0 +1,242 @@
+"""Run the reference's OWN planner graph code on the inputs of the committed golden fixtures and record what it computes.
+
+The planner of younggyoseo/CaDM is the Python in cadm/dynamics/core/utils.py (create_plus_ensemble_cem_mlp :5-250,
+create_plus_cadm_ensemble_cem_mlp :251-565, create_ensemble_pure_context_predictor :569-624, create_dense_layer :635-647)
+written against TensorFlow 1.15, which cannot be installed here.  tests/golden/tf_numpy_shim.py stands in for the ~35 TF
+functions that code uses, with NumPy semantics and eager evaluation; this script imports the UNMODIFIED builder functions
+and environment classes from /root/reference and calls them with arrays where the model classes pass placeholders
+(argument wiring as in core/layers.py:244-272, :300-345 and mlp_cadm_ensemble_cem_dynamics.py:140-210).  The builders run
+the whole CEM loop -- 5 iterations x h steps of the ensemble, rewards, top-k, refit -- and return the planned mean.
+
+For every fixture tests/golden/*.npz (inputs, weights and the oracle's float64 outputs) it injects the same weights and the
+same noise (z per iteration into tf.random.truncated_normal, eps per (iteration, step) into tf.random.normal, in call
+order), runs the reference in float64 and writes tests/golden/recorded/planner_reference.npz: per fixture the final mean
+returned by the reference, and the candidate returns and elite indices of every iteration as seen by tf.nn.top_k.
+A second file, planner_reference_cases.npz, covers what the three fixtures do not: the other environments' reward /
+pre- / post-processing code (pendulum, slim humanoid, crippled half-cheetah, cart-pole, ant with context) and the
+random-shooting branches (continuous, discrete one-hot, with context); their inputs are drawn from a seed by
+tests/reference_cases.py, which the tests use too, so only the reference's outputs are stored.
+tests/test_reference_pinned.py compares the committed fixtures and the oracle with these recordings.
+
+Run in the build container (needs /root/reference):  python tests/golden/make_reference_golden.py
+"""
+import glob
+import os
+import sys
+
+import numpy as np
+
+sys.dont_write_bytecode = True                              # /root/reference is read-only: leave no __pycache__ there
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+import tf_numpy_shim as shim                                # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from reference_cases import CASES, make_case, make_train_batch   # noqa: E402  (inputs of the extra cases, shared with the tests)
+from oracle import philox as ph                             # noqa: E402  (noise specification only: gen_z / gen_eps / ...)
+
+ITERS = 5                                                   # num_cem_iters, core/utils.py:112
+
+
+def reference_env(name):
+    """An instance of the reference's environment class without its simulator: only obs_preproc / obs_postproc /
+    tf_reward_fn are used by the planner graph, and they touch no simulator state."""
+    import cadm.envs as E
+    cls = dict(halfcheetah=E.HalfCheetahEnv, cripple_halfcheetah=E.CrippleHalfCheetahEnv, ant=E.AntEnv,
+               slim_humanoid=E.SlimHumanoidEnv, cartpole=E.RandomCartPole_Force_Length, pendulum=E.RandomPendulumAll)[name]
+    env = cls.__new__(cls)
+    if name == "pendulum":
+        env.max_torque = 2.0                                # gym's PendulumEnv.__init__, which is not run
+    return env
+
+
+def run_fixture(g, U, tf):
+    """g: a mapping with the keys of a golden fixture (+ optional "mode": cem | rs | rs_discrete)."""
+    E, p, n, h, H, m, context, det, seed, C, K = [int(v) for v in g["meta"]]
+    mode = str(g["mode"]) if "mode" in g else "cem"
+    env = reference_env(str(g["envname"]))
+    f8 = np.float64
+    D, A = g["obs"].shape[1], g["mean0"].shape[2]
+    T = shim.TAPE
+    T.__init__()
+    T.dtype = f8
+    for i in range(4):
+        T.variables[f"hidden_{i}_weight"], T.variables[f"hidden_{i}_bias"] = g[f"W{i}"], g[f"b{i}"]
+    T.variables.update(output_mu_weight=g["W_mu"], output_mu_bias=g["b_mu"], output_logvar_weight=g["W_lv"],
+                       output_logvar_bias=g["b_lv"])
+    for nm in ("max_log_var", "max_logvar"):                # the two builders spell the names differently
+        T.variables[nm] = g["max_logvar"].reshape(1, D)
+    for nm in ("min_log_var", "min_logvar"):
+        T.variables[nm] = g["min_logvar"].reshape(1, D)
+    iters = ITERS if mode == "cem" else 1
+    if mode == "cem":
+        z = ph.gen_z(seed, ITERS, m, n, h, A).astype(f8)
+        T.truncated = [z[it] for it in range(ITERS)]
+    elif mode == "rs":
+        T.uniform = [ph.gen_uniform_actions(seed, m, n, h, A).astype(f8)]
+    else:
+        T.uniform = [ph.gen_discrete_actions(seed, m, n, h, A).astype(np.int32)]
+    if not det:
+        eps = ph.gen_eps(seed, iters, h, m, n, p, E, D).astype(f8)
+        T.normal = [None] + [eps[it, t] for it in range(iters) for t in range(h)]      # first draw: the training-batch forward
+    norm = {k: g[f"norm_{k}"].astype(f8) for k in ("obs_mean", "obs_std", "act_mean", "act_std", "delta_mean", "delta_std",
+                                                     "cp_obs_mean", "cp_obs_std", "cp_act_mean", "cp_act_std")}
+    swish = lambda x: x * tf.sigmoid(x)                     # mlp_ensemble_cem_dynamics.py:22
+    common = dict(output_dim=D, hidden_sizes=(H,) * 4, hidden_nonlinearity=swish, output_nonlinearity=tf.identity,
+                  input_obs_dim=D, input_act_dim=A, input_obs_var=g["obs"].astype(f8), input_act_var=np.zeros((m, A)),
+                  n_forwards=h, reward_fn=env.tf_reward_fn(), n_candidates=n, norm_obs_mean_var=norm["obs_mean"],
+                  norm_obs_std_var=norm["obs_std"], norm_act_mean_var=norm["act_mean"], norm_act_std_var=norm["act_std"],
+                  norm_delta_mean_var=norm["delta_mean"], norm_delta_std_var=norm["delta_std"], discrete=mode == "rs_discrete",
+                  ensemble_size=E, bs_input_obs_var=np.zeros((E, 1, D)), bs_input_act_var=np.zeros((E, 1, A)), n_particles=p,
+                  cem_init_mean_var=g["mean0"].astype(f8) if mode == "cem" else None,         # None selects random shooting
+                  cem_init_var_var=g["var0"].astype(f8),
+                  obs_preproc_fn=env.obs_preproc, obs_postproc_fn=env.obs_postproc, deterministic=bool(det),
+                  weight_decays=(0.,) * 5)
+    out = {}
+    if context:
+        for i in range(3):
+            T.variables[f"cp_hidden_{i}_weight"], T.variables[f"cp_hidden_{i}_bias"] = g[f"encW{i}"], g[f"encb{i}"]
+        T.variables["cp_output_weight"], T.variables["cp_output_bias"] = g["encW3"], g["encb3"]
+        hidden = tuple(int(g[f"encW{i}"].shape[2]) for i in range(3))
+        cp_kw = dict(norm_cp_obs_mean_var=norm["cp_obs_mean"], norm_cp_obs_std_var=norm["cp_obs_std"],
+                     norm_cp_act_mean_var=norm["cp_act_mean"], norm_cp_act_std_var=norm["cp_act_std"])
+        bs_ctx, _, cp_forward = U.create_ensemble_pure_context_predictor(
+            context_hidden_sizes=hidden, context_hidden_nonlinearity=tf.nn.relu, output_nonlinearity=tf.identity,
+            ensemble_size=E, cp_input_dim=(D + A) * K, context_weight_decays=(0.,) * 4,
+            bs_input_cp_obs_var=np.zeros((E, 1, D * K)), bs_input_cp_act_var=np.zeros((E, 1, A * K)), cp_output_dim=C, **cp_kw)
+        res = U.create_plus_cadm_ensemble_cem_mlp(
+            input_cp_obs_var=g["cp_obs"].astype(f8), input_cp_act_var=g["cp_act"].astype(f8), bs_input_cp_var=bs_ctx,
+            cp_output_dim=C, cp_forward=cp_forward, build_policy_graph=True, norm_back_delta_mean_var=None,
+            norm_back_delta_std_var=None, **cp_kw, **common)
+        out["plan"] = np.asarray(res[3])
+        # the context of every (member, environment) as the graph computes it for inference (:398-405)
+        out["ctx"] = np.asarray(cp_forward(np.concatenate(
+            [(np.tile(g["cp_obs"].astype(f8)[None], (E, 1, 1)) - norm["cp_obs_mean"]) / (norm["cp_obs_std"] + 1e-10),
+             (np.tile(g["cp_act"].astype(f8)[None], (E, 1, 1)) - norm["cp_act_mean"]) / (norm["cp_act_std"] + 1e-10)], axis=-1),
+            inference=True))
+    else:
+        res = U.create_plus_ensemble_cem_mlp(**common)
+        out["plan"] = np.asarray(res[3])                     # CEM: final mean [m, h, A]; RS: first action of the best candidate
+    assert not T.truncated and not T.normal and not T.uniform, "the graph consumed a different number of draws"
+    if mode == "cem":
+        assert len(T.top_k) == ITERS
+        out["returns"] = np.stack([r for r, _ in T.top_k])  # [iters, m, n]: what tf.nn.top_k was handed
+        out["elites"] = np.stack([i for _, i in T.top_k])   # [iters, m, 50]
+    else:
+        assert len(T.argmax) == 1
+        out["returns"], out["best"] = T.argmax[0]           # [m, n], [m]
+    out["served"] = np.array(T.served)
+    return out
+
+
+def run_train_forward(U, tf):
+    """The forward passes of the TRAINING graph on a bootstrap batch [E, B, .] (what fit() differentiates): context encoder
+    (core/utils.py:605-622), forward model with the context appended (:365-372, outputs mu and the soft-bounded logvar),
+    backward model (deterministic, fed the next observation; mlp_cadm_ensemble_cem_dynamics.py:212-264), and the PE-TS
+    model without context (:73-97).  The planner part of each builder is given a one-step, two-candidate problem."""
+    g = make_train_batch()
+    E, p, n, h, H, m, context, det, seed, C, K = [int(v) for v in g["meta"]]
+    f8 = np.float64
+    env = reference_env("halfcheetah")
+    D, A = g["obs"].shape[1], g["mean0"].shape[2]
+    T = shim.TAPE
+    norm = {k: g[f"norm_{k}"].astype(f8) for k in ("obs_mean", "obs_std", "act_mean", "act_std", "delta_mean", "delta_std",
+                                                     "cp_obs_mean", "cp_obs_std", "cp_act_mean", "cp_act_std", "back_delta_mean",
+                                                     "back_delta_std")}
+    swish = lambda x: x * tf.sigmoid(x)
+
+    def variables(prefix):
+        T.__init__()
+        T.dtype = f8
+        for i in range(4):
+            T.variables[f"hidden_{i}_weight"], T.variables[f"hidden_{i}_bias"] = g[f"{prefix}W{i}"], g[f"{prefix}b{i}"]
+        T.variables.update(output_mu_weight=g[prefix + "W_mu"], output_mu_bias=g[prefix + "b_mu"],
+                           output_logvar_weight=g[prefix + "W_lv"], output_logvar_bias=g[prefix + "b_lv"])
+        for nm, key in (("max_log_var", "max_logvar"), ("max_logvar", "max_logvar"), ("min_log_var", "min_logvar"),
+                        ("min_logvar", "min_logvar")):
+            T.variables[nm] = g[key].reshape(1, D)
+        for i in range(3):
+            T.variables[f"cp_hidden_{i}_weight"], T.variables[f"cp_hidden_{i}_bias"] = g[f"encW{i}"], g[f"encb{i}"]
+        T.variables["cp_output_weight"], T.variables["cp_output_bias"] = g["encW3"], g["encb3"]
+        T.uniform = [ph.gen_uniform_actions(seed, m, n, h, A).astype(f8)]
+        T.normal = [None] * (1 + h)                         # the batch forward and the one planning step: no noise
+
+    def common(obs_batch, deterministic):
+        return dict(output_dim=D, hidden_sizes=(H,) * 4, hidden_nonlinearity=swish, output_nonlinearity=tf.identity,
+                    input_obs_dim=D, input_act_dim=A, input_obs_var=g["obs"].astype(f8), input_act_var=np.zeros((m, A)),
+                    n_forwards=h, reward_fn=env.tf_reward_fn(), n_candidates=n, norm_obs_mean_var=norm["obs_mean"],
+                    norm_obs_std_var=norm["obs_std"], norm_act_mean_var=norm["act_mean"], norm_act_std_var=norm["act_std"],
+                    discrete=False, ensemble_size=E, bs_input_obs_var=obs_batch, bs_input_act_var=g["bs_act"].astype(f8),
+                    n_particles=p, cem_init_mean_var=None, cem_init_var_var=None, obs_preproc_fn=env.obs_preproc,
+                    obs_postproc_fn=env.obs_postproc, deterministic=deterministic, weight_decays=(0.,) * 5)
+
+    cp_kw = dict(norm_cp_obs_mean_var=norm["cp_obs_mean"], norm_cp_obs_std_var=norm["cp_obs_std"],
+                 norm_cp_act_mean_var=norm["cp_act_mean"], norm_cp_act_std_var=norm["cp_act_std"])
+    out = {}
+    variables("")
+    hidden = tuple(int(g[f"encW{i}"].shape[2]) for i in range(3))
+    bs_ctx, _, cp_forward = U.create_ensemble_pure_context_predictor(
+        context_hidden_sizes=hidden, context_hidden_nonlinearity=tf.nn.relu, output_nonlinearity=tf.identity, ensemble_size=E,
+        cp_input_dim=(D + A) * K, context_weight_decays=(0.,) * 4, bs_input_cp_obs_var=g["bs_cp_obs"].astype(f8),
+        bs_input_cp_act_var=g["bs_cp_act"].astype(f8), cp_output_dim=C, **cp_kw)
+    out["ctx"] = np.asarray(bs_ctx)
+    res = U.create_plus_cadm_ensemble_cem_mlp(
+        input_cp_obs_var=g["cp_obs"].astype(f8), input_cp_act_var=g["cp_act"].astype(f8), bs_input_cp_var=bs_ctx, cp_output_dim=C,
+        cp_forward=cp_forward, build_policy_graph=True, norm_delta_mean_var=norm["delta_mean"],
+        norm_delta_std_var=norm["delta_std"], norm_back_delta_mean_var=None, norm_back_delta_std_var=None, **cp_kw,
+        **common(g["bs_obs"].astype(f8), False))
+    out["fwd_mu"], out["fwd_logvar"] = np.asarray(res[4]), np.asarray(res[5])
+    variables("back")
+    res = U.create_plus_cadm_ensemble_cem_mlp(
+        input_cp_obs_var=g["cp_obs"].astype(f8), input_cp_act_var=g["cp_act"].astype(f8), bs_input_cp_var=bs_ctx, cp_output_dim=C,
+        cp_forward=None, build_policy_graph=False, norm_delta_mean_var=None, norm_delta_std_var=None,
+        norm_back_delta_mean_var=norm["back_delta_mean"], norm_back_delta_std_var=norm["back_delta_std"], **cp_kw,
+        **common(g["bs_next"].astype(f8), True))
+    out["back_mu"] = np.asarray(res[4])
+    # PE-TS model: same first-layer shapes are not possible (no context columns), so it gets the leading rows of W0
+    variables("")
+    In = int(g["W0"].shape[1]) - C
+    T.variables["hidden_0_weight"] = g["W0"][:, :In]
+    res = U.create_plus_ensemble_cem_mlp(norm_delta_mean_var=norm["delta_mean"], norm_delta_std_var=norm["delta_std"],
+                                         **common(g["bs_obs"].astype(f8), False))
+    out["pets_mu"], out["pets_logvar"] = np.asarray(res[4]), np.asarray(res[5])
+    return out
+
+
+def main():
+    tf = shim.install(np.float64)
+    sys.path.insert(0, "/root/reference")
+    from cadm.dynamics.core import utils as U
+    blob = {}
+    for path in sorted(glob.glob(os.path.join(HERE, "*.npz"))):
+        name = os.path.splitext(os.path.basename(path))[0]
+        g = np.load(path)
+        out = run_fixture(g, U, tf)
+        scale = np.max(np.abs(g["out_returns"]))
+        print(f"{name}: reference vs committed fixture: returns {np.max(np.abs(out['returns'] - g['out_returns'])) / scale:.2e} "
+              f"(relative), mean {np.max(np.abs(out['plan'] - g['out_mean'])):.2e}, elites equal: "
+              f"{np.array_equal(out['elites'], g['out_elites'])}")
+        for k, v in out.items():
+            blob[f"{name}/{k}"] = v
+    dst = os.path.join(HERE, "recorded", "planner_reference.npz")
+    np.savez_compressed(dst, **blob)
+    print(dst, os.path.getsize(dst), "bytes")
+    blob = {}
+    for name, spec in CASES.items():
+        g = make_case(**spec)
+        out = run_fixture(g, U, tf)
+        print(f"{name}: plan {out['plan'].shape}, returns {out['returns'].shape}, spread of returns "
+              f"{float(out['returns'].min()):.3f} .. {float(out['returns'].max()):.3f}")
+        for k, v in out.items():
+            blob[f"{name}/{k}"] = v
+    for k, v in run_train_forward(U, tf).items():
+        blob[f"train_forward/{k}"] = v
+    print("train_forward:", {k: v.shape for k, v in blob.items() if k.startswith("train_forward/")})
+    dst = os.path.join(HERE, "recorded", "planner_reference_cases.npz")
+    np.savez_compressed(dst, **blob)
+    print(dst, os.path.getsize(dst), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+"""The planner oracle and the committed golden fixtures against recordings of the reference's OWN graph code.
+
+tests/golden/make_reference_golden.py imports the unmodified builder functions of cadm/dynamics/core/utils.py and the
+unmodified environment classes from /root/reference, runs them in float64 over a NumPy stand-in for the TensorFlow
+functions they use (tests/golden/tf_numpy_shim.py) and records what they compute (tests/golden/recorded/planner_*.npz).
+Here: the committed fixtures (which the CUDA engine is tested against on the GPU) and the oracle must reproduce those
+recordings -- candidate returns, elite indices and final plan of every CEM iteration; returns, best candidate and action
+of random shooting -- and the variable creation order of the reference must be the order save() / load() assume.
+CPU only; nothing here reads /root/reference."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from reference_cases import CASES, make_case, make_train_batch
+
+from oracle import cadm_oracle as orc
+from oracle import philox as ph
+from oracle.envs import get_env
+
+REF = np.load(os.path.join(HERE, "golden", "recorded", "planner_reference.npz"))
+REF_CASES = np.load(os.path.join(HERE, "golden", "recorded", "planner_reference_cases.npz"))
+FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(f) for f in FIXTURES])
+def test_committed_fixtures_equal_what_the_reference_graph_computes(path):
+    """The fixtures were written by the oracle; the reference's graph code, fed the same weights and noise, gives the same
+    numbers -- so the GPU test that compares the engine with the fixtures compares it with the reference."""
+    name = os.path.splitext(os.path.basename(path))[0]
+    g = np.load(path)
+    scale = np.max(np.abs(g["out_returns"]))
+    assert np.max(np.abs(REF[f"{name}/returns"] - g["out_returns"])) <= TOL * scale
+    assert np.array_equal(REF[f"{name}/elites"], g["out_elites"])
+    assert np.max(np.abs(REF[f"{name}/plan"] - g["out_mean"])) <= TOL
+    if int(g["meta"][6]):
+        assert np.max(np.abs(REF[f"{name}/ctx"] - g["out_ctx"])) <= TOL * np.max(np.abs(g["out_ctx"]))
+
+
+def _oracle_inputs(g):
+    E, p, n, h, H, m, context, det, seed, C, K = [int(v) for v in g["meta"]]
+    f8 = np.float64
+    env = get_env(str(g["envname"]))
+    prm = orc.DynamicsParams([g[f"W{i}"] for i in range(4)], [g[f"b{i}"] for i in range(4)], g["W_mu"], g["b_mu"], g["W_lv"],
+                             g["b_lv"], g["max_logvar"], g["min_logvar"]).astype(f8)
+    norm = orc.NormStats(*[g[f"norm_{k}"] for k in ("obs_mean", "obs_std", "act_mean", "act_std", "delta_mean", "delta_std",
+                                                     "cp_obs_mean", "cp_obs_std", "cp_act_mean", "cp_act_std")]).astype(f8)
+    ctx_raw = None
+    if context:
+        enc = orc.EncoderParams([g[f"encW{i}"] for i in range(4)], [g[f"encb{i}"] for i in range(4)]).astype(f8)
+        ctx_raw = orc.encode_context(g["cp_obs"].astype(f8), g["cp_act"].astype(f8), enc, norm)
+    return dict(E=E, p=p, n=n, h=h, m=m, det=bool(det), seed=seed), env, prm, norm, ctx_raw
+
+
+@pytest.mark.parametrize("name", [k for k, v in CASES.items() if v["mode"] == "cem"])
+def test_oracle_cem_equals_the_reference_graph_on_the_other_environments(name):
+    g = make_case(**CASES[name])
+    c, env, prm, norm, ctx_raw = _oracle_inputs(g)
+    f8 = np.float64
+    z = ph.gen_z(c["seed"], orc.NUM_CEM_ITERS, c["m"], c["n"], c["h"], env.act_dim).astype(f8)
+    eps = None if c["det"] else ph.gen_eps(c["seed"], orc.NUM_CEM_ITERS, c["h"], c["m"], c["n"], c["p"], c["E"], env.obs_dim).astype(f8)
+    res = orc.cem_plan(g["obs"].astype(f8), g["mean0"].astype(f8), g["var0"].astype(f8), z, prm, norm, env, c["E"], c["p"],
+                       c["det"], eps, ctx_raw)
+    want = REF_CASES[f"{name}/returns"]
+    assert np.max(np.abs(res.returns - want)) <= TOL * np.max(np.abs(want))
+    assert np.array_equal(res.elites, REF_CASES[f"{name}/elites"])
+    assert np.max(np.abs(res.mean - REF_CASES[f"{name}/plan"])) <= TOL
+    assert np.ptp(want) > 1e-3                                       # the case separates candidates at all
+
+
+@pytest.mark.parametrize("name", [k for k, v in CASES.items() if v["mode"] != "cem"])
+def test_oracle_random_shooting_equals_the_reference_graph(name):
+    g = make_case(**CASES[name])
+    c, env, prm, norm, ctx_raw = _oracle_inputs(g)
+    f8 = np.float64
+    discrete = CASES[name]["mode"] == "rs_discrete"
+    if discrete:
+        u = ph.gen_discrete_actions(c["seed"], c["m"], c["n"], c["h"], env.act_dim)
+    else:
+        u = ph.gen_uniform_actions(c["seed"], c["m"], c["n"], c["h"], env.act_dim).astype(f8)
+    eps = ph.gen_eps(c["seed"], 1, c["h"], c["m"], c["n"], c["p"], c["E"], env.obs_dim).astype(f8)[0]
+    res = orc.rs_plan(g["obs"].astype(f8), u, prm, norm, env, c["E"], c["p"], c["det"], eps, ctx_raw, discrete=discrete)
+    want = REF_CASES[f"{name}/returns"]
+    assert np.max(np.abs(res["returns"] - want)) <= TOL * np.max(np.abs(want))
+    assert np.array_equal(res["best"], REF_CASES[f"{name}/best"])
+    assert np.array_equal(np.asarray(res["action"], f8), np.asarray(REF_CASES[f"{name}/plan"], f8))
+    if discrete:
+        assert len(np.unique(want)) > 2                              # some particles crossed the cart-pole limits, some did not
+
+
+def test_the_cases_reach_the_branches_they_are_there_for():
+    """Humanoid: one environment inside the alive band and one outside; pendulum: both sides of the atan2 branch cut."""
+    hum = make_case(**CASES["humanoid_cem"])
+    assert 1.0 < hum["obs"][0, 1] < 2.0 and not 1.0 < hum["obs"][-1, 1] < 2.0
+    r = REF_CASES["humanoid_cem/returns"][0]
+    assert r[0].mean() - r[-1].mean() > 5.0                          # the alive bonus shows in the returns
+    pen = make_case(**CASES["pendulum_cem"])
+    th = np.arctan2(pen["obs"][:, 1], pen["obs"][:, 0])
+    assert th[0] > 3.0 and th[-1] < -3.0
+
+
+def test_variable_creation_order_of_the_reference_is_the_checkpoint_order():
+    """save() dumps tf.trainable_variables() in creation order (mlp_cadm_ensemble_cem_dynamics.py:571-577); the names below
+    are what the reference's builders asked for, in order, when run by the generator.  cadm_b200's `params` list -- encoder
+    (W, b) per layer, hidden (W, b) per layer, mu head, logvar head, max_logvar, min_logvar -- must follow it."""
+    served = [str(s) for s in REF["hc_cadm_small/served"]]
+    enc = [f"cp_hidden_{i}_{w}" for i in range(3) for w in ("weight", "bias")] + ["cp_output_weight", "cp_output_bias"]
+    dyn = [f"hidden_{i}_{w}" for i in range(4) for w in ("weight", "bias")] + \
+          ["output_mu_weight", "output_mu_bias", "output_logvar_weight", "output_logvar_bias"]
+    assert served == enc + dyn + ["max_logvar", "min_logvar"]
+    assert [str(s) for s in REF["hc_pets_small/served"]] == dyn + ["max_log_var", "min_log_var"]
+
+
+def test_stand_in_ops_follow_the_tensorflow_rules_the_planner_depends_on():
+    """The few places where the NumPy stand-in has to choose a convention: top_k and argmax tie-breaking (lower index first),
+    the floored modulo, softplus for large arguments, gather along axis 0."""
+    import tf_numpy_shim as shim
+    shim.TAPE.__init__()
+    vals, idx = shim.top_k(np.array([[1.0, 3.0, 3.0, 2.0, 3.0]]), k=3)
+    assert idx.tolist() == [[1, 2, 4]] and idx.dtype == np.int32 and vals.tolist() == [[3.0, 3.0, 3.0]]
+    assert shim.argmax(np.array([[0.0, 2.0, 2.0]]), 1, output_type=np.int32).tolist() == [1]
+    assert np.isclose(shim.softplus(np.array([800.0, -800.0, 0.0])), [800.0, 0.0, np.log(2.0)]).all()
+    assert shim.gather(np.arange(12).reshape(4, 3), np.array([3, 0])).tolist() == [[9, 10, 11], [0, 1, 2]]
+    assert shim.reshape(np.arange(6), np.array([2, 3], np.int32)).shape == (2, 3)
+    shim.TAPE.truncated = [np.full((2,), 0.5)]
+    assert shim.random_truncated_normal([2], 1.0, 2.0).tolist() == [2.0, 2.0]
+    with pytest.raises(RuntimeError):
+        shim.random_normal([2])
+
+
+def test_training_forward_passes_equal_the_reference_graph():
+    """What fit() differentiates (cadm_b200/dynamics/training.py, PyTorch) against the reference's training graph on a
+    bootstrap batch: the context encoder, the forward model's mu and soft-bounded logvar with the context appended, the
+    deterministic backward model fed the next observation, and the PE-TS model without context."""
+    import torch
+    from cadm_b200.dynamics.training import CaDMTrainer, EnsembleNLLTrainer
+    g = make_train_batch()
+    C = int(g["meta"][9])
+    D = g["obs"].shape[1]
+    f8 = lambda a: np.asarray(a, np.float64)
+    mlp = lambda pre: dict(W=[f8(g[f"{pre}W{i}"]) for i in range(4)], b=[f8(g[f"{pre}b{i}"]) for i in range(4)],
+                           W_mu=f8(g[pre + "W_mu"]), b_mu=f8(g[pre + "b_mu"]), W_lv=f8(g[pre + "W_lv"]), b_lv=f8(g[pre + "b_lv"]),
+                           max_logvar=f8(g["max_logvar"]).reshape(1, D), min_logvar=f8(g["min_logvar"]).reshape(1, D))
+    enc = dict(W=[f8(g[f"encW{i}"]) for i in range(4)], b=[f8(g[f"encb{i}"]) for i in range(4)])
+    stats = [f8(g[f"norm_{k}"]) for k in ("obs_mean", "obs_std", "act_mean", "act_std", "delta_mean", "delta_std", "cp_obs_mean",
+                                          "cp_obs_std", "cp_act_mean", "cp_act_std", "back_delta_mean", "back_delta_std")]
+    tr = CaDMTrainer(enc, mlp(""), mlp("back"), "halfcheetah", False, (0.,) * 5, (0.,) * 4, 0.0, 0.5, 1e-3, dtype=torch.float64)
+    t = lambda a: torch.as_tensor(f8(a))
+    st = [t(s_) for s_ in stats]
+    want = lambda k: REF_CASES[f"train_forward/{k}"]
+    close = lambda got, ref: np.max(np.abs(got.detach().numpy() - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
+    with torch.no_grad():
+        ctx = tr.context(t(g["bs_cp_obs"]), t(g["bs_cp_act"]), st)
+        assert close(ctx, want("ctx"))
+        mu, lv = tr.fwd.forward(t(g["bs_obs"]), t(g["bs_act"]), st, ctx)
+        assert close(mu, want("fwd_mu")) and close(lv, want("fwd_logvar"))
+        back_mu, _ = tr.back.forward(t(g["bs_next"]), t(g["bs_act"]), st, ctx)
+        assert close(back_mu, want("back_mu"))
+        pets = mlp("")
+        pets["W"][0] = pets["W"][0][:, :pets["W"][0].shape[1] - C]
+        mu, lv = EnsembleNLLTrainer(pets, "halfcheetah", False, (0.,) * 5, 0.0, 1e-3, dtype=torch.float64).forward(
+            t(g["bs_obs"]), t(g["bs_act"]), st[:6])
+        assert close(mu, want("pets_mu")) and close(lv, want("pets_logvar"))
+    lv = want("fwd_logvar")
+    assert 0.4 < lv.max() < 0.5 and -10.0 < lv.min() < -9.0          # both soft bounds were reached
