@@ -6,7 +6,8 @@ pyprind, which this container lacks.  Both are replaced by inert stand-ins in sy
 or copied), the reference classes are imported from /root/reference and driven with the stand-in environment and policy
 of tests/sampler_fakes.py.  Recorded per scenario: every argument of every policy.get_actions() call, the finished paths,
 and the arrays process_samples() returns; for the evaluation rollouts of `cadm/samplers/utils.py` (rollout_multi,
-context_rollout_multi) the calls and the returned average.  tests/test_samplers.py replays the same scenarios through cadm_b200's classes.
+context_rollout_multi) the calls and the returned average; for `cadm/policies/mpc_controller.py` which arguments reach
+dynamics_model.get_action(), in which order, for every (context, use_cem) combination.  tests/test_samplers.py replays the same scenarios through cadm_b200's classes.
 
 Run in the build container (needs /root/reference):  python tests/golden/make_sampler_golden.py
 """
@@ -21,7 +22,7 @@ sys.dont_write_bytecode = True                              # /root/reference is
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from sampler_fakes import FakeEnv, ScriptedPolicy          # noqa: E402
+from sampler_fakes import FakeEnv, ScriptedPolicy, controller_dispatch_log          # noqa: E402
 
 SCENARIOS = dict(
     # name: (context, state_diff, use_cem, history_length, future_length, num_rollouts, max_path_length, horizon)
@@ -128,6 +129,8 @@ def main():
     for name in EVAL_SCENARIOS:
         for k, v in run_eval(name).items():
             blob[f"{name}/{k}"] = v
+    from cadm.policies.mpc_controller import MPCController
+    blob["mpc_controller/dispatch"] = np.array(controller_dispatch_log(MPCController))
     path = os.path.join(HERE, "recorded", "sampler_golden.npz")
     np.savez_compressed(path, **blob)
     print(path, len(blob), "arrays", os.path.getsize(path), "bytes")

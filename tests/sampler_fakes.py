@@ -80,3 +80,44 @@ class ScriptedPolicy:
             sol = np.sin(s[:, None, None] + 0.37 * grid) * 0.8 + 0.5 * np.asarray(init_mean) + 0.1 * np.asarray(init_var)
             return np.clip(sol, -1.0, 1.0), []
         return np.clip(np.sin(s[:, None] + 0.37 * grid[0, 0][None, :]), -1.0, 1.0), []
+
+
+class RecordingDynamicsModel:
+    """get_action() records which positional arguments it was given (by tag) and returns a constant."""
+
+    def __init__(self):
+        self.calls = []
+
+    def get_action(self, *args, **kwargs):
+        self.calls.append((tuple(str(a[0]) if isinstance(a, tuple) else repr(a) for a in args), tuple(sorted(kwargs))))
+        return np.zeros((1, 1))
+
+
+class RewardEnv:
+    """The only thing MPCController asks of its environment: a `reward` attribute (mpc_controller.py:34)."""
+    action_space = _Box(2)
+
+    def reward(self, obs, act, next_obs):
+        return 0.0
+
+
+def controller_dispatch_log(controller_cls):
+    """Every (context, use_cem) combination through get_actions(), and get_action() for both planners: the tags of the
+    arguments that reach dynamics_model.get_action, in order."""
+    log = []
+    tag = lambda s: (s,)                     # a tuple so that the recorder can tell the inputs apart
+    for context in (False, True):
+        for use_cem in (False, True):
+            dm = RecordingDynamicsModel()
+            c = controller_cls(name="policy", env=RewardEnv(), dynamics_model=dm, use_cem=use_cem, context=context)
+            _, info = c.get_actions(tag("obs"), cp_obs=tag("cp_obs"), cp_act=tag("cp_act"), init_mean=tag("mean"),
+                                    init_var=tag("var"))
+            log.append(("get_actions", context, use_cem, dm.calls[-1], type(info).__name__))
+    for use_cem in (False, True):
+        dm = RecordingDynamicsModel()
+        c = controller_cls(name="policy", env=RewardEnv(), dynamics_model=dm, use_cem=use_cem, context=False)
+        obs = np.zeros(3)
+        _, info = c.get_action(obs, init_mean=tag("mean"), init_var=tag("var"))
+        args = dm.calls[-1][0]
+        log.append(("get_action", False, use_cem, (("obs[None]",) + args[1:], dm.calls[-1][1]), type(info).__name__))
+    return repr(log)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from sampler_fakes import FakeEnv, ScriptedPolicy
+from sampler_fakes import FakeEnv, ScriptedPolicy, controller_dispatch_log
 
 from cadm_b200.samplers import (HostPlannerState, IterativeEnvExecutor, ModelSampleProcessor, Sampler, context_rollout_multi,
                                 discount_cumsum, rollout_multi)
@@ -208,3 +208,12 @@ def test_evaluation_rollouts_match_the_reference(name):
         for k, v in call.items():
             _same(v, g(f"call{i}_{k}"), (i, k))
     assert float(avg) == float(g("average"))
+
+
+def test_mpc_controller_dispatches_like_the_reference():
+    """cadm/policies/mpc_controller.py: which of (obs, cp_obs, cp_act, init_mean, init_var) reach dynamics_model.get_action,
+    and in which order, for every (context, use_cem) combination -- recorded from the reference class."""
+    from cadm_b200.policies.mpc_controller import MPCController
+    got = controller_dispatch_log(MPCController)
+    assert got == str(GOLDEN["mpc_controller/dispatch"])
+    assert "('obs', 'cp_obs', 'cp_act', 'mean', 'var')" in got and "('obs', 'mean', 'var')" in got
