@@ -51,16 +51,16 @@ def reference_env(name):
     return env
 
 
-def run_fixture(g, U, tf):
-    """g: a mapping with the keys of a golden fixture (+ optional "mode": cem | rs | rs_discrete)."""
+def run_fixture(g, U, tf, f8=np.float64):
+    """g: a mapping with the keys of a golden fixture (+ optional "mode": cem | rs | rs_discrete); f8: the float type the
+    whole graph runs in."""
     E, p, n, h, H, m, context, det, seed, C, K = [int(v) for v in g["meta"]]
     mode = str(g["mode"]) if "mode" in g else "cem"
     env = reference_env(str(g["envname"]))
-    f8 = np.float64
     D, A = g["obs"].shape[1], g["mean0"].shape[2]
     T = shim.TAPE
     T.__init__()
-    T.dtype = f8
+    T.dtype = tf.float32 = f8
     for i in range(4):
         T.variables[f"hidden_{i}_weight"], T.variables[f"hidden_{i}_bias"] = g[f"W{i}"], g[f"b{i}"]
     T.variables.update(output_mu_weight=g["W_mu"], output_mu_bias=g["b_mu"], output_logvar_weight=g["W_lv"],
@@ -84,11 +84,11 @@ def run_fixture(g, U, tf):
                                                      "cp_obs_mean", "cp_obs_std", "cp_act_mean", "cp_act_std")}
     swish = lambda x: x * tf.sigmoid(x)                     # mlp_ensemble_cem_dynamics.py:22
     common = dict(output_dim=D, hidden_sizes=(H,) * 4, hidden_nonlinearity=swish, output_nonlinearity=tf.identity,
-                  input_obs_dim=D, input_act_dim=A, input_obs_var=g["obs"].astype(f8), input_act_var=np.zeros((m, A)),
+                  input_obs_dim=D, input_act_dim=A, input_obs_var=g["obs"].astype(f8), input_act_var=np.zeros((m, A), f8),
                   n_forwards=h, reward_fn=env.tf_reward_fn(), n_candidates=n, norm_obs_mean_var=norm["obs_mean"],
                   norm_obs_std_var=norm["obs_std"], norm_act_mean_var=norm["act_mean"], norm_act_std_var=norm["act_std"],
                   norm_delta_mean_var=norm["delta_mean"], norm_delta_std_var=norm["delta_std"], discrete=mode == "rs_discrete",
-                  ensemble_size=E, bs_input_obs_var=np.zeros((E, 1, D)), bs_input_act_var=np.zeros((E, 1, A)), n_particles=p,
+                  ensemble_size=E, bs_input_obs_var=np.zeros((E, 1, D), f8), bs_input_act_var=np.zeros((E, 1, A), f8), n_particles=p,
                   cem_init_mean_var=g["mean0"].astype(f8) if mode == "cem" else None,         # None selects random shooting
                   cem_init_var_var=g["var0"].astype(f8),
                   obs_preproc_fn=env.obs_preproc, obs_postproc_fn=env.obs_postproc, deterministic=bool(det),
@@ -104,7 +104,7 @@ def run_fixture(g, U, tf):
         bs_ctx, _, cp_forward = U.create_ensemble_pure_context_predictor(
             context_hidden_sizes=hidden, context_hidden_nonlinearity=tf.nn.relu, output_nonlinearity=tf.identity,
             ensemble_size=E, cp_input_dim=(D + A) * K, context_weight_decays=(0.,) * 4,
-            bs_input_cp_obs_var=np.zeros((E, 1, D * K)), bs_input_cp_act_var=np.zeros((E, 1, A * K)), cp_output_dim=C, **cp_kw)
+            bs_input_cp_obs_var=np.zeros((E, 1, D * K), f8), bs_input_cp_act_var=np.zeros((E, 1, A * K), f8), cp_output_dim=C, **cp_kw)
         res = U.create_plus_cadm_ensemble_cem_mlp(
             input_cp_obs_var=g["cp_obs"].astype(f8), input_cp_act_var=g["cp_act"].astype(f8), bs_input_cp_var=bs_ctx,
             cp_output_dim=C, cp_forward=cp_forward, build_policy_graph=True, norm_back_delta_mean_var=None,
@@ -219,6 +219,15 @@ def main():
               f"{np.array_equal(out['elites'], g['out_elites'])}")
         for k, v in out.items():
             blob[f"{name}/{k}"] = v
+        # the same graph in float32 (NumPy's float32 kernels, not TensorFlow's): pins the oracle's float32 mode and shows
+        # what single precision costs the reference's own formulation
+        o32 = run_fixture(g, U, tf, np.float32)
+        assert o32["returns"].dtype == np.float32 and o32["plan"].dtype == np.float32
+        print(f"{name}: float32 graph vs float64 graph: returns {np.max(np.abs(o32['returns'] - out['returns'])) / scale:.2e} "
+              f"(relative), mean {np.max(np.abs(o32['plan'] - out['plan'])):.2e}, elites equal: "
+              f"{np.array_equal(o32['elites'], out['elites'])}")
+        for k in ("plan", "returns", "elites"):
+            blob[f"{name}/f32_{k}"] = o32[k]
     dst = os.path.join(HERE, "recorded", "planner_reference.npz")
     np.savez_compressed(dst, **blob)
     print(dst, os.path.getsize(dst), "bytes")

@@ -43,6 +43,38 @@ def test_committed_fixtures_equal_what_the_reference_graph_computes(path):
         assert np.max(np.abs(REF[f"{name}/ctx"] - g["out_ctx"])) <= TOL * np.max(np.abs(g["out_ctx"]))
 
 
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(f) for f in FIXTURES])
+def test_oracle_float32_mode_equals_the_reference_graph_run_in_float32(path):
+    """The oracle is dtype-generic; run in float32 it follows the reference graph run in float32 (NumPy float32 kernels under
+    both) step for step, and both stay within ~1e-7 of the float64 results on these problems: the 1e-4 parity tolerance is
+    room for a different float32 summation order (tensor cores, split operands), not for a different formulation."""
+    name = os.path.splitext(os.path.basename(path))[0]
+    g = np.load(path)
+    E, p, n, h, H, m, context, det, seed, C, K = [int(v) for v in g["meta"]]
+    t = np.float32
+    env = get_env(str(g["envname"]))
+    prm = orc.DynamicsParams([g[f"W{i}"] for i in range(4)], [g[f"b{i}"] for i in range(4)], g["W_mu"], g["b_mu"], g["W_lv"],
+                             g["b_lv"], g["max_logvar"], g["min_logvar"]).astype(t)
+    norm = orc.NormStats(*[g[f"norm_{k}"] for k in ("obs_mean", "obs_std", "act_mean", "act_std", "delta_mean", "delta_std",
+                                                     "cp_obs_mean", "cp_obs_std", "cp_act_mean", "cp_act_std")]).astype(t)
+    ctx_raw = None
+    if context:
+        enc = orc.EncoderParams([g[f"encW{i}"] for i in range(4)], [g[f"encb{i}"] for i in range(4)]).astype(t)
+        ctx_raw = orc.encode_context(g["cp_obs"].astype(t), g["cp_act"].astype(t), enc, norm)
+    z = ph.gen_z(seed, orc.NUM_CEM_ITERS, m, n, h, env.act_dim).astype(t)
+    eps = None if det else ph.gen_eps(seed, orc.NUM_CEM_ITERS, h, m, n, p, E, env.obs_dim).astype(t)
+    res = orc.cem_plan(g["obs"].astype(t), g["mean0"].astype(t), g["var0"].astype(t), z, prm, norm, env, E, p, bool(det), eps, ctx_raw)
+    assert res.returns.dtype == np.float32
+    scale = np.max(np.abs(g["out_returns"]))
+    # the same bits on two of the three fixtures; on the third, 0.2 % of the last iteration's returns differ by one float32
+    # ulp (NumPy's float32 reductions depend on the memory layout of their input, which the two programs do not share)
+    assert np.max(np.abs(res.returns - REF[f"{name}/f32_returns"])) <= 2.5e-7 * scale
+    assert np.array_equal(res.elites, REF[f"{name}/f32_elites"])
+    assert np.max(np.abs(res.mean - REF[f"{name}/f32_plan"])) <= 2.5e-7
+    assert np.max(np.abs(REF[f"{name}/f32_returns"] - REF[f"{name}/returns"])) / scale < 1e-6
+    assert np.array_equal(REF[f"{name}/f32_elites"], REF[f"{name}/elites"])
+
+
 def _oracle_inputs(g):
     E, p, n, h, H, m, context, det, seed, C, K = [int(v) for v in g["meta"]]
     f8 = np.float64
