@@ -322,3 +322,38 @@ def test_many_candidates_sort_path_and_sharding():
             os.environ.pop("CADM_TC_VARIANT", None)
         else:
             os.environ["CADM_TC_VARIANT"] = old
+
+
+def test_env_sharding_virtual_ranks(precision):
+    """SURVEY 8(e), the alternative for m >= G: blocks of environments planned independently (EnvShardedPlanner, two
+    virtual ranks on one device, ragged 2 + 1, injected z / eps in the global layouts) give the rows of the unsharded
+    decision.  The rollout kernel may differ with the local batch size, so the comparison is to fp32 rounding (TOL), with
+    the elite margin rule of the other CEM tests."""
+    from cadm_b200.parallel import EnvShardedPlanner
+    from cadm_b200.synth import synthetic_inputs
+    model, env, cfg = _model("C2", precision=precision, candidates=64)
+    m = 3
+    inp = synthetic_inputs(env, m, cfg["horizon"], False, seed=4)
+    E, p, n, h, D, A = cfg["ensemble"], cfg["particles"], 64, cfg["horizon"], env.obs_dim, env.act_dim
+    z = ph.gen_z(9, orc.NUM_CEM_ITERS, m, n, h, A)
+    eps = ph.gen_eps(9, orc.NUM_CEM_ITERS, h, m, n, p, E, D)
+    full = model.engine.plan_cem(inp["obs"], inp["init_mean"], inp["init_var"], seed=0, z=z, eps=eps)
+    full = {k: v.cpu().numpy() for k, v in full.items()}
+    for rank in range(2):
+        planner = EnvShardedPlanner(model.engine, rank=rank, world=2, gather=False)
+        out = planner.plan(inp["obs"], inp["init_mean"], inp["init_var"], seed=0, z=z, eps=eps, logs=True)
+        assert out["bounds"] == [0, 2, 3] and planner.collectives == 0
+        lo, hi = out["bounds"][rank], out["bounds"][rank + 1]
+        rets, el = out["returns"].cpu().numpy(), out["elites"].cpu().numpy()
+        same = True
+        for it in range(orc.NUM_CEM_ITERS):
+            want = full["returns"][it, lo:hi]
+            assert np.max(np.abs(rets[it] - want)) / np.max(np.abs(want)) < TOL, (rank, it)
+            if not np.array_equal(el[it], full["elites"][it, lo:hi]):
+                ok, gap, e = elite_margin_ok(want.astype(np.float64), None, rets[it], orc.NUM_ELITES)
+                assert not ok, (rank, it, gap, e)          # only a boundary tie may change the selection
+                same = False
+                break
+        if same:
+            assert np.max(np.abs(out["mean"].cpu().numpy() - full["mean"][lo:hi])) < TOL
+            assert np.max(np.abs(out["var"].cpu().numpy() - full["var"][lo:hi])) < TOL
