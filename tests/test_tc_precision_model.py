@@ -91,3 +91,51 @@ def test_full_width_rollout_split_against_float64(monkeypatch):
         errs[terms] = float(np.max(np.abs(got - want) / rms))
     assert errs[3] < TOL / 10, errs
     assert errs[1] > 20 * errs[3], errs
+
+
+def test_cheaper_arithmetic_is_not_robust_to_the_weight_scale(monkeypatch):
+    """Two tempting shortcuts for the hidden-layer epilogue, screened with the model before spending GPU time on them:
+    a one-MUFU swish (0.5x tanh.approx(0.5x) + 0.5x, tanh.approx.f32 is specified to 2^-11 relative) and fp16-only activations
+    (drop X_lo: no lo split, half the operand stores).  On random-init weights both stay inside the 1e-4 bar; with the hidden
+    weights scaled x2 (a less contractive, trained-like network) both leave it by a wide margin, while the three-term split with
+    an fp32-accurate swish does not move.  Hence the kernels keep ex2 + rcp and the full split."""
+    env = get_env("halfcheetah")
+    f8 = np.float64
+
+    def dense_xhi(x, W, b, act=None):
+        xh, _ = tc_model.split_f16(np.asarray(x, np.float32) * tc_model.X_SCALE)
+        wh, wl = tc_model.split_f16(np.asarray(W, np.float32) * tc_model.W_SCALE)
+        out = (np.matmul(xh, wh) + np.matmul(xh, wl)) * np.float32(1 / 512) + np.asarray(b, np.float32)
+        return act(out) if act is not None else out
+
+    def swish_tanh(x):
+        hx = np.float32(0.5) * x
+        return hx * (np.tanh(hx) * (1 + np.float32(2.0 ** -11))) + hx
+
+    plain_swish = orc.swish
+    variants = dict(tc3x=(tc_model.dense_split(3), plain_swish), tanh=(tc_model.dense_split(3), swish_tanh),
+                    xhi=(dense_xhi, plain_swish))
+    errs = {}
+    for wscale in (1.0, 2.0):
+        rng = np.random.default_rng(7)
+        E, p, n, h, m = 5, 20, 4, 30, 1
+        prm = orc.init_dynamics_params(rng, E, env.proc_obs_dim + env.act_dim, 200, env.obs_dim, dtype=np.float32)
+        prm.b_lv[...] = -6.0
+        for W in prm.W:
+            W *= np.float32(wscale)
+        norm = orc.NormStats(np.zeros(18), np.ones(18), np.zeros(6), np.full(6, 0.6), np.zeros(18), np.full(18, 0.1)).astype(np.float32)
+        obs = (0.1 * rng.standard_normal((m, 18))).astype(np.float32)
+        acts = rng.uniform(-1, 1, (m, n, h, 6)).astype(np.float32)
+        eps = ph.gen_eps(3, 1, h, m, n, p, E, 18)[0]
+        _, want = orc.rollout(obs.astype(f8), acts.astype(f8), prm.astype(f8), norm.astype(f8), env, E, p, False, eps.astype(f8),
+                              trace=True)
+        rms = np.sqrt(np.mean(want ** 2, axis=(0, 1, 2, 3)))
+        for name, (dense, act) in variants.items():
+            with monkeypatch.context() as mp:
+                mp.setattr(orc, "dense", dense)
+                mp.setattr(orc, "swish", act)
+                _, got = orc.rollout(obs, acts, prm, norm, env, E, p, False, eps, trace=True)
+            errs[name, wscale] = float(np.max(np.abs(got - want) / rms))
+    assert errs["tc3x", 1.0] < TOL / 20 and errs["tc3x", 2.0] < TOL / 20, errs
+    assert errs["tanh", 1.0] < TOL and errs["xhi", 1.0] < TOL, errs
+    assert errs["tanh", 2.0] > TOL and errs["xhi", 2.0] > TOL, errs
