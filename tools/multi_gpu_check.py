@@ -1,5 +1,6 @@
 """Run under torchrun on G GPUs: candidate-sharded CEM must give, on every rank, exactly the plan a single rank computes
-for the same global problem (n = 200 G candidates) -- with the fused peer-memory all-gather and with NCCL."""
+for the same global problem (n = 200 G candidates) -- with the fused peer-memory all-gather and with NCCL; and
+environment-sharded CEM (EnvShardedPlanner) must reproduce the single-process decision for 2 G environments."""
 import os
 import sys
 
@@ -43,6 +44,28 @@ for fused in (True, False):
     if rank == 0:
         print(f"[{'fused' if fused else 'nccl '}] plans identical on all {world} ranks: {same_all}; NCCL all-gathers per decision: "
               f"{planner.collectives // 3}")
+# ---- environment sharding (m >= G): every rank plans a block of environments on a world = 1 engine, injected
+# noise in the global layouts; the gathered plan must equal the single-process decision to fp32 rounding (the kernel is
+# picked from the local batch) and be the same on every rank
+from cadm_b200.parallel import EnvShardedPlanner
+from oracle import philox as ph                           # noise specification only (this is a check script, not the product)
+m_env, n_env = 2 * world, 64
+model, env, cfg = build_model("C2", m_max=m_env, candidates=n_env, device=f"cuda:{local}")
+inp = synthetic_inputs(env, m_env, 30, False, seed=5)
+z = ph.gen_z(13, 5, m_env, n_env, 30, env.act_dim)
+eps = ph.gen_eps(13, 5, 30, m_env, n_env, cfg["particles"], cfg["ensemble"], env.obs_dim)
+planner = EnvShardedPlanner(model.engine, gather=True)
+out = planner.plan(inp["obs"], inp["init_mean"], inp["init_var"], seed=0, z=z, eps=eps)
+full = model.engine.plan_cem(inp["obs"], inp["init_mean"], inp["init_var"], seed=0, z=z, eps=eps)
+torch.cuda.synchronize()
+err = float((out["mean"] - full["mean"]).abs().max())
+gathered = [torch.empty_like(out["mean"]) for _ in range(world)]
+dist.all_gather(gathered, out["mean"])
+same_all = all(torch.equal(g, gathered[0]) for g in gathered)
+ok &= same_all and err < 1e-4 and planner.collectives == 1
+if rank == 0:
+    print(f"[envs ] {m_env} environments over {world} ranks: max |plan - single-process plan| = {err:.2e}; identical on all ranks: "
+          f"{same_all}; collectives per decision: {planner.collectives}")
 if rank == 0:
     print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
 dist.destroy_process_group()
