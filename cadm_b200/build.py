@@ -24,6 +24,10 @@ NVCC_FLAGS = [
 ]
 
 
+# Experiments only (e.g. CADM_EXTRA_NVCC_FLAGS="-DCADM_SPLIT_FHADD=1"): extra flags enter the digest, so switching them rebuilds.
+EXTRA_FLAGS = os.environ.get("CADM_EXTRA_NVCC_FLAGS", "").split()
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -35,7 +39,7 @@ def _digest():
             h.update(f.encode())
             h.update(open(os.path.join(CSRC, f), "rb").read())
     h.update(open(os.path.join(HERE, "..", "include", "cadm_b200.h"), "rb").read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -50,7 +54,7 @@ def build(force=False, verbose=False):
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [nvcc_path()] + NVCC_FLAGS + EXTRA_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -142,9 +142,17 @@ constexpr float kWScale = 64.0f;       // weights are stored as 64 w     -> accu
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     uint32_t h;
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));   // low half <- x0
+#if defined(CADM_SPLIT_FHADD) && CADM_SPLIT_FHADD
+    // Experimental (off by default, not yet measured on the device): mixed-precision add of PTX ISA 8.6 -- neg.f16 + add.f32.f16
+    // fold into one FHADD per value, the same x - float(h) bit for bit (tools/probes/split_fhadd.cu).
+    float r0, r1;
+    asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tneg.f16 a, a;\n\tneg.f16 b, b;\n\tadd.f32.f16 %0, a, %3;\n\tadd.f32.f16 %1, b, %4;\n\t}"
+        : "=f"(r0), "=f"(r1) : "r"(h), "f"(x0), "f"(x1));
+#else
     float h0, h1;
     asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}" : "=f"(h0), "=f"(h1) : "r"(h));
     const float r0 = x0 - h0, r1 = x1 - h1;
+#endif
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
     hi = h;
 }
