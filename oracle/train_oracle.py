@@ -4,10 +4,13 @@ PE-TS: cadm/dynamics/core/utils.py:73-97 (forward on the bootstrap batch, soft-b
 cadm/dynamics/mlp_ensemble_cem_dynamics.py:150-167 (mse / mu / var / reg / l2 losses).  CaDM: core/utils.py:605-622
 (encoder), :365-372 (input with the context appended), mlp_cadm_ensemble_cem_dynamics.py:266-314 (joint loss with the
 backward model) and :676-696 (flattening of the future_length-step samples, written here as explicit loops).  The forward passes (encoder,
-forward model with context, backward model, PE-TS model) of cadm_b200/dynamics/training.py are pinned by the reference's
-own builder functions run over the NumPy TensorFlow stand-in (tests/test_reference_pinned.py); the few lines that turn mu /
-logvar into the scalar losses live in the reference's model constructors, which cannot be run here: those are restated
-below and pinned by closed-form cases and finite differences in tests/test_training.py."""
+forward model with context, backward model, PE-TS model) of cadm_b200/dynamics/training.py and every scalar loss the
+reference's model constructors define (mse, backward mse, the l2 terms with their per-layer decay indices, mu / var / reg /
+recon / total) are pinned by the reference's own code run over the NumPy TensorFlow stand-in: the unmodified builder
+functions and the unmodified MLPEnsembleCEMDynamicsModel classes of both modules, instantiated with their placeholders served
+as values (tests/golden/make_reference_golden.py run_train_forward / run_model_losses, tests/test_reference_pinned.py).  The
+functions below must reproduce those recordings to 1e-12; closed-form cases and finite differences in tests/test_training.py
+remain as independent checks."""
 import numpy as np
 
 

@@ -204,6 +204,110 @@ def run_train_forward(U, tf):
     return out
 
 
+class _Optimizer:
+    """Stands for tf.compat.v1.train.AdamOptimizer in the model constructors (an `optimizer=` argument of theirs)."""
+
+    def __init__(self, learning_rate):
+        self.learning_rate = learning_rate
+
+    def minimize(self, loss):
+        return None
+
+
+LOSS_CASES = [dict(deterministic=False, back_coeff=0.5), dict(deterministic=True, back_coeff=0.5),
+              dict(deterministic=False, back_coeff=0.0)]
+LOSS_DECAYS = dict(weight_decays=(1e-3, 2e-3, 3e-3, 4e-3, 5e-3), context_weight_decays=(6e-3, 7e-3, 8e-3, 9e-3),
+                   weight_decay_coeff=0.7)
+
+
+def run_model_losses(tf):
+    """The scalar training losses as the reference's MODEL CONSTRUCTORS define them
+    (mlp_ensemble_cem_dynamics.py:140-167; mlp_cadm_ensemble_cem_dynamics.py:266-314), on the bootstrap batch of
+    reference_cases.make_train_batch: the unmodified classes are instantiated with every placeholder served its value in
+    creation order (the graph is evaluated while it is built), an inert optimizer, non-zero weight decays, and a one-step
+    random-shooting planner so that the policy part of the graph stays small.  Returns {case/loss_name: float}."""
+    from cadm.dynamics.mlp_cadm_ensemble_cem_dynamics import MLPEnsembleCEMDynamicsModel as CaDMModel
+    from cadm.dynamics.mlp_ensemble_cem_dynamics import MLPEnsembleCEMDynamicsModel as PETSModel
+    import types
+    g = make_train_batch()
+    E, p, n, h, H, m, context, det, seed, C, K = [int(v) for v in g["meta"]]
+    f8 = np.float64
+    D, A = g["obs"].shape[1], g["mean0"].shape[2]
+    env = reference_env("halfcheetah")
+    env.observation_space = types.SimpleNamespace(shape=(D,))
+    env.action_space = types.SimpleNamespace(shape=(A,))
+    env.proc_observation_space_dims = int(g["norm_obs_mean"].shape[0])
+    T = shim.TAPE
+    norm = {k: g[f"norm_{k}"].astype(f8) for k in ("obs_mean", "obs_std", "act_mean", "act_std", "delta_mean", "delta_std",
+                                                     "cp_obs_mean", "cp_obs_std", "cp_act_mean", "cp_act_std", "back_delta_mean",
+                                                     "back_delta_std")}
+    rng = np.random.default_rng(77)
+    bs_delta = rng.standard_normal((E, g["bs_obs"].shape[1], D)) * 0.1          # targets: any numbers do
+    bs_back_delta = rng.standard_normal((E, g["bs_obs"].shape[1], D)) * 0.1
+
+    def variables(C_cols):
+        T.__init__()
+        T.dtype = tf.float32 = f8
+        for scope, pre in (("ff_model", ""), ("backward_model", "back")):
+            for i in range(4):
+                W = g[f"{pre}W{i}"]
+                if i == 0 and C_cols == 0:
+                    W = W[:, :W.shape[1] - C]                                    # the PE-TS model has no context columns
+                T.variables[f"{scope}/hidden_{i}_weight"], T.variables[f"{scope}/hidden_{i}_bias"] = W, g[f"{pre}b{i}"]
+            T.variables.update({f"{scope}/output_mu_weight": g[pre + "W_mu"], f"{scope}/output_mu_bias": g[pre + "b_mu"],
+                                f"{scope}/output_logvar_weight": g[pre + "W_lv"], f"{scope}/output_logvar_bias": g[pre + "b_lv"]})
+        for nm, key in (("max_log_var", "max_logvar"), ("max_logvar", "max_logvar"), ("min_log_var", "min_logvar"),
+                        ("min_logvar", "min_logvar")):
+            T.variables[nm] = g[key].reshape(1, D)
+        for i in range(3):
+            T.variables[f"cp_hidden_{i}_weight"], T.variables[f"cp_hidden_{i}_bias"] = g[f"encW{i}"], g[f"encb{i}"]
+        T.variables["cp_output_weight"], T.variables["cp_output_bias"] = g["encW3"], g["encb3"]
+
+    def pick(model, names):
+        return {k: float(np.asarray(getattr(model, k))) for k in names if hasattr(model, k)}
+
+    names = ("mse_loss", "back_mse_loss", "l2_reg_loss", "context_l2_reg_loss", "back_l2_reg_loss", "l2_loss", "mu_loss", "var_loss",
+             "reg_loss", "recon_loss", "loss")
+    hidden = tuple(int(g[f"encW{i}"].shape[2]) for i in range(3))
+    common = dict(hidden_sizes=(H,) * 4, hidden_nonlinearity="swish", optimizer=_Optimizer, n_forwards=h, n_candidates=n,
+                  ensemble_size=E, n_particles=p, use_cem=False, weight_decays=LOSS_DECAYS["weight_decays"],
+                  weight_decay_coeff=LOSS_DECAYS["weight_decay_coeff"])
+    out = {}
+    for case in LOSS_CASES:
+        det_, bc = case["deterministic"], case["back_coeff"]
+        variables(C)
+        # placeholder creation order of mlp_cadm_ensemble_cem_dynamics.py:109-137
+        T.placeholders = [g["obs"], g["obs"], np.zeros((m, A)), g["cp_obs"], g["cp_act"],
+                          g["bs_obs"], g["bs_next"], g["bs_act"], bs_delta, bs_back_delta, g["bs_cp_obs"], g["bs_cp_act"],
+                          norm["obs_mean"], norm["obs_std"], norm["act_mean"], norm["act_std"], norm["delta_mean"], norm["delta_std"],
+                          norm["cp_obs_mean"], norm["cp_obs_std"], norm["cp_act_mean"], norm["cp_act_std"],
+                          norm["back_delta_mean"], norm["back_delta_std"],
+                          np.zeros((m, h, A)), np.full((m, h, A), 0.25)]
+        T.uniform = [ph.gen_uniform_actions(seed, m, n, h, A).astype(f8)]
+        T.normal = [None] * (0 if det_ else 1 + h)
+        model = CaDMModel("dm", env, cp_hidden_sizes=hidden, context_weight_decays=LOSS_DECAYS["context_weight_decays"],
+                          context_out_dim=C, history_length=K, future_length=1, state_diff=True, back_coeff=bc,
+                          deterministic=det_, **common)
+        assert not T.placeholders and not T.uniform and not T.normal
+        tag = f"cadm_{'det' if det_ else 'prob'}_back{bc}"
+        for k, v in pick(model, names).items():
+            out[f"{tag}/{k}"] = v
+    for det_ in (False, True):
+        variables(0)
+        # placeholder creation order of mlp_ensemble_cem_dynamics.py:90-107
+        T.placeholders = [g["obs"], np.zeros((m, A)), np.zeros((m, D)), g["bs_obs"], g["bs_act"], bs_delta,
+                          norm["obs_mean"], norm["obs_std"], norm["act_mean"], norm["act_std"], norm["delta_mean"], norm["delta_std"],
+                          np.zeros((m, h, A)), np.full((m, h, A), 0.25)]
+        T.uniform = [ph.gen_uniform_actions(seed, m, n, h, A).astype(f8)]
+        T.normal = [None] * (0 if det_ else 1 + h)
+        model = PETSModel("dm", env, deterministic=det_, **common)
+        assert not T.placeholders and not T.uniform and not T.normal
+        for k, v in pick(model, names).items():
+            out[f"pets_{'det' if det_ else 'prob'}/{k}"] = v
+    out["targets/bs_delta"], out["targets/bs_back_delta"] = bs_delta, bs_back_delta
+    return out
+
+
 def main():
     tf = shim.install(np.float64)
     sys.path.insert(0, "/root/reference")
@@ -242,6 +346,10 @@ def main():
     for k, v in run_train_forward(U, tf).items():
         blob[f"train_forward/{k}"] = v
     print("train_forward:", {k: v.shape for k, v in blob.items() if k.startswith("train_forward/")})
+    losses = run_model_losses(tf)
+    for k, v in losses.items():
+        blob[f"model_losses/{k}"] = np.asarray(v)
+    print("model_losses:", {k: round(float(v), 6) for k, v in losses.items() if np.ndim(v) == 0})
     dst = os.path.join(HERE, "recorded", "planner_reference_cases.npz")
     np.savez_compressed(dst, **blob)
     print(dst, os.path.getsize(dst), "bytes")

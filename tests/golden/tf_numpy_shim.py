@@ -32,6 +32,9 @@ class Tape:
         self.top_k = []              # (input, indices) of every tf.nn.top_k call
         self.argmax = []             # (input, indices) of every tf.argmax call
         self.served = []             # names of the variables handed out, in creation order
+        self.scope = []              # variable_scope stack (names)
+        self.placeholders = []       # FIFO queue of arrays served by tf.compat.v1.placeholder, in creation order
+        self.served_scoped = []      # the same names with their scope path
 
 
 TAPE = Tape()
@@ -147,7 +150,11 @@ def random_uniform(shape, minval=0, maxval=None, dtype=None, seed=None, name=Non
 # ---- variables (from a table, by name)
 def _serve(name, initial=None, want_shape=None):
     TAPE.served.append(name)
-    if name in TAPE.variables:
+    TAPE.served_scoped.append("/".join(TAPE.scope + [name]))
+    scoped = [f"{sc}/{name}" for sc in reversed(TAPE.scope) if f"{sc}/{name}" in TAPE.variables]
+    if scoped:                       # "<scope>/<name>" wins over the bare name (two models with equal variable names)
+        v = np.asarray(TAPE.variables[scoped[0]], dtype=TAPE.dtype)
+    elif name in TAPE.variables:
         v = np.asarray(TAPE.variables[name], dtype=TAPE.dtype)
     elif initial is not None:
         v = np.asarray(initial, dtype=TAPE.dtype)
@@ -164,6 +171,41 @@ def Variable(initial_value=None, dtype=None, name=None, trainable=True):
 
 def get_variable(name, shape=None, initializer=None, dtype=None, trainable=True):
     return _serve(name, want_shape=shape)
+
+
+class variable_scope:
+    """tf.compat.v1.variable_scope as a plain name stack (no reuse rules: variables come from a table)."""
+
+    def __init__(self, name, reuse=None, **k):
+        self.name = name
+
+    def __enter__(self):
+        TAPE.scope.append(self.name)
+        return self
+
+    def __exit__(self, *a):
+        TAPE.scope.pop()
+        return False
+
+
+def placeholder(dtype=None, shape=None, name=None):
+    """The model constructors create placeholders and build the graph on them; here the graph is evaluated eagerly, so a
+    placeholder IS its value: the next array of the injected queue (creation order), checked against the declared shape."""
+    if not TAPE.placeholders:
+        raise RuntimeError("the constructor created more placeholders than values were injected")
+    v = np.asarray(TAPE.placeholders.pop(0), dtype=TAPE.dtype)
+    if shape is not None:
+        assert v.ndim == len(shape) and all(d is None or int(d) == n for d, n in zip(shape, v.shape)), (shape, v.shape)
+    return v
+
+
+class _Graph:
+    def get_name_scope(self):
+        return "/".join(TAPE.scope)
+
+
+class _GraphKeys:
+    TRAINABLE_VARIABLES = "trainable_variables"
 
 
 def _initializer(*a, **k):
@@ -226,7 +268,9 @@ def install(dtype=np.float64):
     tf.random = _module("tensorflow.random", normal=random_normal, truncated_normal=random_truncated_normal,
                         uniform=random_uniform)
     tf.contrib = _module("tensorflow.contrib", layers=_module("tensorflow.contrib.layers", xavier_initializer=_initializer))
-    v1 = _module("tensorflow.compat.v1", get_variable=get_variable, Variable=Variable)
+    v1 = _module("tensorflow.compat.v1", get_variable=get_variable, Variable=Variable, placeholder=placeholder,
+                 variable_scope=variable_scope, AUTO_REUSE=object(), trainable_variables=lambda: list(TAPE.served_scoped),
+                 get_default_graph=lambda: _Graph(), get_collection=lambda key, scope=None: [], GraphKeys=_GraphKeys)
     v1.train = _Stub("tensorflow.compat.v1.train")
     tf.compat = _module("tensorflow.compat", v1=v1)
     tf.train = _Stub("tensorflow.train")

@@ -201,3 +201,66 @@ def test_training_forward_passes_equal_the_reference_graph():
         assert close(mu, want("pets_mu")) and close(lv, want("pets_logvar"))
     lv = want("fwd_logvar")
     assert 0.4 < lv.max() < 0.5 and -10.0 < lv.min() < -9.0          # both soft bounds were reached
+
+
+MODEL_LOSS_CASES = [("cadm_prob_back0.5", False, 0.5), ("cadm_det_back0.5", True, 0.5), ("cadm_prob_back0.0", False, 0.0)]
+LOSS_DECAYS = dict(weight_decays=(1e-3, 2e-3, 3e-3, 4e-3, 5e-3), context_weight_decays=(6e-3, 7e-3, 8e-3, 9e-3),
+                   weight_decay_coeff=0.7)           # as in tests/golden/make_reference_golden.py
+
+
+def _loss_inputs():
+    g = make_train_batch()
+    C, D = int(g["meta"][9]), g["obs"].shape[1]
+    f8 = lambda a: np.asarray(a, np.float64)
+    mlp = lambda pre: dict(W=[f8(g[f"{pre}W{i}"]) for i in range(4)], b=[f8(g[f"{pre}b{i}"]) for i in range(4)],
+                           W_mu=f8(g[pre + "W_mu"]), b_mu=f8(g[pre + "b_mu"]), W_lv=f8(g[pre + "W_lv"]), b_lv=f8(g[pre + "b_lv"]),
+                           max_logvar=f8(g["max_logvar"]).reshape(1, D), min_logvar=f8(g["min_logvar"]).reshape(1, D))
+    enc = dict(W=[f8(g[f"encW{i}"]) for i in range(4)], b=[f8(g[f"encb{i}"]) for i in range(4)])
+    stats = [f8(g[f"norm_{k}"]) for k in ("obs_mean", "obs_std", "act_mean", "act_std", "delta_mean", "delta_std", "cp_obs_mean",
+                                          "cp_obs_std", "cp_act_mean", "cp_act_std", "back_delta_mean", "back_delta_std")]
+    batch = (f8(g["bs_obs"]), f8(g["bs_act"]), REF_CASES["model_losses/targets/bs_delta"], f8(g["bs_next"]),
+             REF_CASES["model_losses/targets/bs_back_delta"], f8(g["bs_cp_obs"]), f8(g["bs_cp_act"]))
+    return g, C, mlp, enc, stats, batch
+
+
+def _check_losses(tag, got):
+    keys = [k.split("/")[-1] for k in REF_CASES.files if k.startswith(f"model_losses/{tag}/")]
+    assert {"mse_loss", "recon_loss", "loss", "l2_reg_loss"} <= set(keys)
+    for k in keys:
+        want = float(REF_CASES[f"model_losses/{tag}/{k}"])
+        assert abs(float(got[k]) - want) <= 1e-12 * max(1.0, abs(want)), (tag, k, float(got[k]), want)
+
+
+@pytest.mark.parametrize("tag,det,back_coeff", MODEL_LOSS_CASES)
+def test_cadm_training_losses_equal_the_reference_model_constructor(tag, det, back_coeff):
+    """Every scalar the reference's CaDM model constructor defines (mlp_cadm_ensemble_cem_dynamics.py:266-314: mse, backward
+    mse, the three l2 terms, mu / var / reg / recon / total loss), recorded from the UNMODIFIED class instantiated over the
+    TensorFlow stand-in, against what fit() minimises (CaDMTrainer.losses) and against the NumPy restatement."""
+    import torch
+    from cadm_b200.dynamics.training import CaDMTrainer
+    from oracle import train_oracle
+    g, C, mlp, enc, stats, batch = _loss_inputs()
+    d = LOSS_DECAYS
+    tr = CaDMTrainer(enc, mlp(""), mlp("back"), "halfcheetah", det, d["weight_decays"], d["context_weight_decays"],
+                     d["weight_decay_coeff"], back_coeff, 1e-3, dtype=torch.float64)
+    with torch.no_grad():
+        _check_losses(tag, tr.losses(*batch, stats))
+    _check_losses(tag, train_oracle.cadm_losses(enc, mlp(""), mlp("back"), "halfcheetah", det, d["weight_decays"],
+                                                d["context_weight_decays"], d["weight_decay_coeff"], back_coeff, *batch, stats))
+
+
+@pytest.mark.parametrize("tag,det", [("pets_prob", False), ("pets_det", True)])
+def test_pets_training_losses_equal_the_reference_model_constructor(tag, det):
+    """The same for the PE-TS / vanilla model (mlp_ensemble_cem_dynamics.py:140-167)."""
+    import torch
+    from cadm_b200.dynamics.training import EnsembleNLLTrainer
+    from oracle import train_oracle
+    g, C, mlp, enc, stats, batch = _loss_inputs()
+    d = LOSS_DECAYS
+    dyn = mlp("")
+    dyn["W"][0] = dyn["W"][0][:, :dyn["W"][0].shape[1] - C]
+    tr = EnsembleNLLTrainer(dyn, "halfcheetah", det, d["weight_decays"], d["weight_decay_coeff"], 1e-3, dtype=torch.float64)
+    with torch.no_grad():
+        _check_losses(tag, tr.losses(batch[0], batch[1], batch[2], stats[:6]))
+    _check_losses(tag, train_oracle.pets_losses(dyn, "halfcheetah", det, d["weight_decays"], d["weight_decay_coeff"], batch[0],
+                                                batch[1], batch[2], stats[:6]))
