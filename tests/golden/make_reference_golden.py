@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 import tf_numpy_shim as shim                                # noqa: E402
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from reference_cases import CASES, make_case, make_train_batch   # noqa: E402  (inputs of the extra cases, shared with the tests)
+from reference_cases import CASES, FIT_REPLAY, make_case, make_fit_data, make_train_batch   # noqa: E402  (inputs of the extra cases, shared with the tests)
 from oracle import philox as ph                             # noqa: E402  (noise specification only: gen_z / gen_eps / ...)
 
 ITERS = 5                                                   # num_cem_iters, core/utils.py:112
@@ -308,6 +308,107 @@ def run_model_losses(tf):
     return out
 
 
+class _Session:
+    """Stands for the TF session inside fit(): records what every sess.run is fed (by placeholder attribute name) and answers
+    with scripted losses -- the training step's are constants, the validation recon loss follows FIT_REPLAY['valid_script']."""
+
+    def __init__(self, model, script):
+        self.names = {id(v): k[:-3] for k, v in vars(model).items() if k.endswith("_ph")}
+        self.script, self.calls, self.n_valid = list(script), [], 0
+
+    def run(self, fetches, feed_dict=None):
+        train = fetches[-1] is None                      # the train_op of the inert optimizer
+        self.calls.append(("train" if train else "valid", {self.names[id(k)]: np.array(v, np.float64) for k, v in feed_dict.items()}))
+        n = len(fetches) - (1 if train else 0)           # mse, [back mse,] recon
+        if train:
+            return [0.25] * n + [None]
+        self.n_valid += 1
+        return [0.5] * (n - 1) + [self.script[self.n_valid - 1]]
+
+
+def run_fit_replay(tf):
+    """fit() of both UNMODIFIED reference model classes (mlp_ensemble_cem_dynamics.py:209-323,
+    mlp_cadm_ensemble_cem_dynamics.py:382-569) on reference_cases.make_fit_data, with NumPy's global generator seeded and the
+    session replaced by a recorder: everything fit() does in NumPy -- targets, dataset bookkeeping, normalisation statistics,
+    validation split, flattening of the future steps, per-member bootstrap indices, per-epoch reshuffling, minibatches, the
+    early-stopping rule -- is recorded as the sequence of feeds and the number of epochs run."""
+    from cadm.dynamics.mlp_cadm_ensemble_cem_dynamics import MLPEnsembleCEMDynamicsModel as CaDMModel
+    from cadm.dynamics.mlp_ensemble_cem_dynamics import MLPEnsembleCEMDynamicsModel as PETSModel
+    import types
+    c = FIT_REPLAY
+    data = make_fit_data()
+    f8 = np.float64
+    env = reference_env("halfcheetah")
+    D, A = 18, 6
+    env.observation_space = types.SimpleNamespace(shape=(D,))
+    env.action_space = types.SimpleNamespace(shape=(A,))
+    P = env.proc_observation_space_dims = D
+    E, H, K, F, C = c["E"], c["H"], c["K"], c["F"], c["C"]
+    T = shim.TAPE
+    rng = np.random.default_rng(5)
+    out = {}
+
+    def build(cls, context):
+        T.__init__()
+        T.dtype = tf.float32 = f8
+        In = P + A + (C if context else 0)
+        sizes = [In, H, H]
+        for scope in ("ff_model", "backward_model"):
+            for i in range(2):
+                T.variables[f"{scope}/hidden_{i}_weight"] = rng.standard_normal((E, sizes[i], sizes[i + 1])) * 0.1
+                T.variables[f"{scope}/hidden_{i}_bias"] = np.zeros((E, 1, sizes[i + 1]))
+            for head in ("mu", "logvar"):
+                T.variables[f"{scope}/output_{head}_weight"] = rng.standard_normal((E, H, D)) * 0.1
+                T.variables[f"{scope}/output_{head}_bias"] = np.zeros((E, 1, D))
+        for nm in ("max_log_var", "max_logvar"):
+            T.variables[nm] = np.full((1, D), 0.5)
+        for nm in ("min_log_var", "min_logvar"):
+            T.variables[nm] = np.full((1, D), -10.0)
+        enc_sizes = [(D + A) * K, 8, 8, 8, C]
+        for i in range(3):
+            T.variables[f"cp_hidden_{i}_weight"] = rng.standard_normal((E, enc_sizes[i], enc_sizes[i + 1])) * 0.1
+            T.variables[f"cp_hidden_{i}_bias"] = np.zeros((E, 1, enc_sizes[i + 1]))
+        T.variables["cp_output_weight"], T.variables["cp_output_bias"] = rng.standard_normal((E, 8, C)) * 0.1, np.zeros((E, 1, C))
+        m, h, n, B = 1, 1, 2, 2
+        z = lambda *shape: np.zeros(shape)
+        o = lambda *shape: np.ones(shape)
+        if context:
+            T.placeholders = [z(m, D), z(m, D), z(m, A), z(m, D * K), z(m, A * K),
+                              z(E, B, D), z(E, B, D), z(E, B, A), z(E, B, D), z(E, B, D), z(E, B, D * K), z(E, B, A * K),
+                              z(P), o(P), z(A), o(A), z(D), o(D), z(D * K), o(D * K), z(A * K), o(A * K), z(D), o(D),
+                              z(m, h, A), o(m, h, A)]
+        else:
+            T.placeholders = [z(m, D), z(m, A), z(m, D), z(E, B, D), z(E, B, A), z(E, B, D),
+                              z(P), o(P), z(A), o(A), z(D), o(D), z(m, h, A), o(m, h, A)]
+        T.uniform = [ph.gen_uniform_actions(1, m, n, h, A).astype(f8)]
+        T.normal = [None] * (1 + h)
+        kw = dict(hidden_sizes=(H, H), hidden_nonlinearity="swish", optimizer=_Optimizer, n_forwards=h, n_candidates=n,
+                  ensemble_size=E, n_particles=E, use_cem=False, batch_size=c["batch_size"], weight_decays=(0.,) * 3)
+        if context:
+            kw.update(cp_hidden_sizes=(8, 8, 8), context_weight_decays=(0.,) * 4, context_out_dim=C, history_length=K,
+                      future_length=F, state_diff=False, back_coeff=0.5)
+        return cls("dm", env, **kw)
+
+    for tag, cls, context in (("pets", PETSModel, False), ("cadm", CaDMModel, True)):
+        model = build(cls, context)
+        sess = _Session(model, c["valid_script"])
+        tf.compat.v1.get_default_session = lambda sess=sess: sess
+        np.random.seed(c["np_seed"])
+        if context:
+            model.fit(data["obs"], data["act"], data["obs_next"], data["cp_obs"], data["cp_act"], data["future_bool"],
+                      epochs=c["epochs"], rolling_average_persitency=c["persistency"])
+        else:                                            # the PE-TS model trains on single steps: the first of each sample
+            model.fit(data["obs"][:, :D], data["act"][:, :A], data["obs_next"][:, :D], epochs=c["epochs"],
+                      rolling_average_persitency=c["persistency"])
+        out[f"{tag}/kinds"] = np.array([k for k, _ in sess.calls])
+        for i, (_, feed) in enumerate(sess.calls):
+            for k, v in feed.items():
+                if not k.startswith("norm_") or i == 0:                        # the statistics do not change within one fit()
+                    out[f"{tag}/call{i:03d}/{k}"] = v
+        out[f"{tag}/valid_runs"] = np.array(sess.n_valid)
+    return out
+
+
 def main():
     tf = shim.install(np.float64)
     sys.path.insert(0, "/root/reference")
@@ -346,6 +447,11 @@ def main():
     for k, v in run_train_forward(U, tf).items():
         blob[f"train_forward/{k}"] = v
     print("train_forward:", {k: v.shape for k, v in blob.items() if k.startswith("train_forward/")})
+    replay = run_fit_replay(tf)
+    for k, v in replay.items():
+        blob[f"fit_replay/{k}"] = v
+    print("fit_replay:", {t: (list(replay[f"{t}/kinds"]).count("train"), int(replay[f"{t}/valid_runs"])) for t in ("pets", "cadm")},
+          "(training steps, epochs)")
     losses = run_model_losses(tf)
     for k, v in losses.items():
         blob[f"model_losses/{k}"] = np.asarray(v)

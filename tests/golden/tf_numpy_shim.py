@@ -196,7 +196,18 @@ def placeholder(dtype=None, shape=None, name=None):
     v = np.asarray(TAPE.placeholders.pop(0), dtype=TAPE.dtype)
     if shape is not None:
         assert v.ndim == len(shape) and all(d is None or int(d) == n for d, n in zip(shape, v.shape)), (shape, v.shape)
-    return v
+    return v.view(_Placeholder)                      # hashable by identity: the models use placeholders as feed_dict keys
+
+
+class _Placeholder(np.ndarray):
+    """Identity-hashable view.  Arithmetic on it yields plain arrays / NumPy scalars (as on the plain arrays the builders are
+    otherwise handed), so that `x += y` on a derived 0-d result rebinds instead of writing through -- TF tensors are
+    immutable, and the model constructors rely on it (`recon_loss = self.mse_loss; recon_loss += ...`)."""
+    __hash__ = object.__hash__
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        plain = tuple(np.asarray(i) if isinstance(i, _Placeholder) else i for i in inputs)
+        return getattr(ufunc, method)(*plain, **kwargs)
 
 
 class _Graph:

@@ -88,3 +88,24 @@ def make_train_batch(seed=31, E=3, B=7, H=24):
              norm_back_delta_mean=(0.01 * rng.standard_normal(D)).astype(np.float32),
              norm_back_delta_std=rng.uniform(0.05, 0.2, D).astype(np.float32))
     return g
+
+
+FIT_REPLAY = dict(E=3, H=16, K=3, F=2, C=4, batch_size=16, n=45, epochs=6, persistency=0.5, np_seed=4321,
+                  valid_script=[1.0, 0.9, 5.0, 0.1, 0.1, 0.1])
+
+
+def make_fit_data(seed=41):
+    """Transitions for the fit-loop replay (tests/golden/make_reference_golden.py run_fit_replay and
+    tests/test_reference_pinned.py): n samples of F consecutive steps with a K-step history, ragged future masks."""
+    c = FIT_REPLAY
+    env = get_env("halfcheetah")
+    D, A, n, F, K = env.obs_dim, env.act_dim, c["n"], c["F"], c["K"]
+    rng = np.random.default_rng(seed)
+    obs = rng.standard_normal((n, F * D)) * 0.5
+    act = rng.uniform(-1, 1, (n, F * A))
+    obs_next = obs + 0.1 * rng.standard_normal((n, F * D))
+    cp_obs = rng.standard_normal((n, K * D)) * 0.3
+    cp_act = rng.uniform(-1, 1, (n, K * A))
+    future_bool = np.ones((n, F))
+    future_bool[rng.random(n) < 0.3, 1:] = 0.0          # paths that end before the second future step
+    return dict(obs=obs, act=act, obs_next=obs_next, cp_obs=cp_obs, cp_act=cp_act, future_bool=future_bool)

@@ -264,3 +264,89 @@ def test_pets_training_losses_equal_the_reference_model_constructor(tag, det):
         _check_losses(tag, tr.losses(batch[0], batch[1], batch[2], stats[:6]))
     _check_losses(tag, train_oracle.pets_losses(dyn, "halfcheetah", det, d["weight_decays"], d["weight_decay_coeff"], batch[0],
                                                 batch[1], batch[2], stats[:6]))
+
+
+class _LegacyRng:
+    """The Generator interface fit_ensemble / fit_cadm_ensemble draw from, forwarded to NumPy's global legacy generator, which
+    is what the reference's fit() uses (np.random.permutation / randint / uniform): the same seed gives the same draws."""
+
+    @staticmethod
+    def permutation(n):
+        return np.random.permutation(n)
+
+    @staticmethod
+    def integers(lo, hi, size):
+        return np.random.randint(lo, hi, size=size)
+
+    @staticmethod
+    def uniform(size):
+        return np.random.uniform(size=size)
+
+
+class _RecordingTrainer:
+    """Stands where the reference has its session: records what every training / validation step is fed and answers with the
+    scripted losses of the recording."""
+
+    calls, script = [], []
+
+    def __init__(self, *a, **k):
+        pass
+
+    def train_step(self, *batch_and_stats):
+        type(self).calls.append(("train", batch_and_stats))
+        return (0.25,) * (2 if len(batch_and_stats) == 4 else 3)
+
+    def evaluate(self, *batch_and_stats):
+        type(self).calls.append(("valid", batch_and_stats))
+        n_valid = sum(k == "valid" for k, _ in type(self).calls)
+        return (0.5,) * (1 if len(batch_and_stats) == 4 else 2) + (type(self).script[n_valid - 1],)
+
+    def export(self, *a):
+        pass
+
+
+@pytest.mark.parametrize("tag", ["pets", "cadm"])
+def test_fit_loop_feeds_what_the_reference_fit_feeds(tag, monkeypatch):
+    """fit() of the UNMODIFIED reference classes was run with NumPy's global generator seeded and its session replaced by a
+    recorder (make_reference_golden.py run_fit_replay).  Here fit_ensemble / fit_cadm_ensemble run on the same data with the same
+    generator and a recording trainer: every minibatch of every epoch (per-member bootstrap rows after the per-epoch reshuffle,
+    future steps flattened and masked), the validation batches, the normalisation statistics and the epoch at which the
+    early-stopping rule fires must be the reference's, bit for bit."""
+    from reference_cases import FIT_REPLAY, make_fit_data
+    from test_training import _CpuCadmModel, _CpuModel
+    from cadm_b200.dynamics import training
+    c, data = FIT_REPLAY, make_fit_data()
+    D, A = 18, 6
+    _RecordingTrainer.calls, _RecordingTrainer.script = [], list(c["valid_script"])
+    monkeypatch.setattr(training, "EnsembleNLLTrainer", _RecordingTrainer)
+    monkeypatch.setattr(training, "CaDMTrainer", _RecordingTrainer)
+    np.random.seed(c["np_seed"])
+    kw = dict(epochs=c["epochs"], rolling_average_persitency=c["persistency"], rng=_LegacyRng(), device="cpu", log=lambda *_: None)
+    if tag == "pets":
+        model = _CpuModel("halfcheetah", E=c["E"], H=c["H"], batch_size=c["batch_size"])
+        info = training.fit_ensemble(model, data["obs"][:, :D], data["act"][:, :A], data["obs_next"][:, :D], **kw)
+        names = ("bs_obs", "bs_act", "bs_delta")
+        stat_names = ("obs_mean", "obs_std", "act_mean", "act_std", "delta_mean", "delta_std")
+    else:
+        model = _CpuCadmModel("halfcheetah", E=c["E"], H=c["H"], K=c["K"], F=c["F"], C=c["C"], back_coeff=0.5, batch_size=c["batch_size"])
+        info = training.fit_cadm_ensemble(model, data["obs"], data["act"], data["obs_next"], data["cp_obs"], data["cp_act"],
+                                          data["future_bool"], **kw)
+        names = ("bs_obs", "bs_act", "bs_delta", "bs_obs_next", "bs_back_delta", "bs_cp_obs", "bs_cp_act")
+        stat_names = ("obs_mean", "obs_std", "act_mean", "act_std", "delta_mean", "delta_std", "cp_obs_mean", "cp_obs_std",
+                      "cp_act_mean", "cp_act_std", "back_delta_mean", "back_delta_std")
+    rec = lambda k: REF_CASES[f"fit_replay/{tag}/{k}"]
+    kinds = [k for k, _ in _RecordingTrainer.calls]
+    assert kinds == list(rec("kinds")) and info["epochs"] == int(rec("valid_runs")) == 3
+    assert kinds.count("train") > kinds.count("valid") == 3                       # several minibatches per epoch
+    for i, (_, fed) in enumerate(_RecordingTrainer.calls):
+        *batch, stats = fed
+        assert len(batch) == len(names)
+        for name, got in zip(names, batch):
+            want = rec(f"call{i:03d}/{name}")
+            assert got.shape == want.shape and np.array_equal(np.asarray(got, np.float64), want), (tag, i, name)
+        if i == 0:
+            for name, got in zip(stat_names, stats):
+                assert np.array_equal(np.asarray(got, np.float64), rec(f"call000/norm_{name}")), (tag, name)
+    if tag == "cadm":                                                              # the ragged future masks removed rows
+        n_rows = sum(b[0].shape[1] for k, b in _RecordingTrainer.calls[:4] if k == "train")
+        assert n_rows < int(0.8 * c["n"]) * c["F"] + 1
