@@ -48,12 +48,13 @@ for fused in (True, False):
 # noise in the global layouts; the gathered plan must equal the single-process decision to fp32 rounding (the kernel is
 # picked from the local batch) and be the same on every rank
 from cadm_b200.parallel import EnvShardedPlanner
-from oracle import philox as ph                           # noise specification only (this is a check script, not the product)
+import numpy as np
 m_env, n_env = 2 * world, 64
 model, env, cfg = build_model("C2", m_max=m_env, candidates=n_env, device=f"cuda:{local}")
 inp = synthetic_inputs(env, m_env, 30, False, seed=5)
-z = ph.gen_z(13, 5, m_env, n_env, 30, env.act_dim)
-eps = ph.gen_eps(13, 5, 30, m_env, n_env, cfg["particles"], cfg["ensemble"], env.obs_dim)
+noise = np.random.default_rng(13)                         # same seed on every rank: identical injected noise
+z = np.clip(noise.standard_normal((5, m_env, n_env, 30, env.act_dim)), -2, 2).astype(np.float32)
+eps = noise.standard_normal((5, 30, cfg["ensemble"], cfg["particles"] // cfg["ensemble"] * m_env * n_env, env.obs_dim)).astype(np.float32)
 planner = EnvShardedPlanner(model.engine, gather=True)
 out = planner.plan(inp["obs"], inp["init_mean"], inp["init_var"], seed=0, z=z, eps=eps)
 full = model.engine.plan_cem(inp["obs"], inp["init_mean"], inp["init_var"], seed=0, z=z, eps=eps)
