@@ -33,7 +33,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 import tf_numpy_shim as shim                                # noqa: E402
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from reference_cases import CASES, FIT_REPLAY, make_case, make_fit_data, make_train_batch   # noqa: E402  (inputs of the extra cases, shared with the tests)
+from reference_cases import (CASES, FIT_REPLAY, GET_ACTION_CASES, get_action_inputs, make_case, make_fit_data,   # noqa: E402
+                             make_train_batch)   # inputs of the extra cases, shared with the tests
 from oracle import philox as ph                             # noqa: E402  (noise specification only: gen_z / gen_eps / ...)
 
 ITERS = 5                                                   # num_cem_iters, core/utils.py:112
@@ -409,6 +410,95 @@ def run_fit_replay(tf):
     return out
 
 
+class _ActionSession:
+    """The session inside get_action(): records the feed of the compiled planner function and answers with a scripted,
+    deliberately out-of-range action."""
+
+    def __init__(self, model, answer):
+        self.names = {id(v): k[:-3] for k, v in vars(model).items() if k.endswith("_ph")}
+        self.answer, self.feeds = answer, []
+
+    def run(self, fetches, feed_dict=None):
+        self.feeds.append({self.names[id(k)]: np.array(v, np.float64) for k, v in feed_dict.items()})
+        return np.array(self.answer)
+
+
+def run_get_action(tf):
+    """get_action() of both UNMODIFIED model classes (mlp_ensemble_cem_dynamics.py:191-207,
+    mlp_cadm_ensemble_cem_dynamics.py:344-367): which statistics reach the compiled planner function in which slot
+    (normalize_input on / off, state_diff, discrete actions), what else is fed, and what comes back (clip for continuous
+    actions only)."""
+    from cadm.dynamics.mlp_cadm_ensemble_cem_dynamics import MLPEnsembleCEMDynamicsModel as CaDMModel
+    from cadm.dynamics.mlp_ensemble_cem_dynamics import MLPEnsembleCEMDynamicsModel as PETSModel
+    import types
+    from collections import OrderedDict
+    f8 = np.float64
+    T = shim.TAPE
+    rng = np.random.default_rng(9)
+    out = {}
+    for name, spec in GET_ACTION_CASES.items():
+        x = get_action_inputs(name, spec)
+        D, A, P, K, h, m = (x[k] for k in ("D", "A", "P", "K", "h", "m"))
+        context = spec["kind"] == "cadm"
+        env = reference_env(spec["envname"])
+        env.observation_space = types.SimpleNamespace(shape=(D,))
+        env.action_space = types.SimpleNamespace(shape=(), n=A) if x["discrete"] else types.SimpleNamespace(shape=(A,))
+        env.proc_observation_space_dims = P
+        E, H, C = 2, 8, 4
+        for use_cem in ([False] if x["discrete"] else [True, False]):
+            T.__init__()
+            T.dtype = tf.float32 = f8
+            In = P + A + (C if context else 0)
+            for i, (a, b) in enumerate(((In, H), (H, H))):
+                T.variables[f"hidden_{i}_weight"], T.variables[f"hidden_{i}_bias"] = rng.standard_normal((E, a, b)) * 0.1, np.zeros((E, 1, b))
+            for head in ("mu", "logvar"):
+                T.variables[f"output_{head}_weight"], T.variables[f"output_{head}_bias"] = rng.standard_normal((E, H, D)) * 0.1, np.zeros((E, 1, D))
+            for nm in ("max_log_var", "max_logvar"):
+                T.variables[nm] = np.full((1, D), 0.5)
+            for nm in ("min_log_var", "min_logvar"):
+                T.variables[nm] = np.full((1, D), -10.0)
+            sizes = [(D + A) * K, 8, 8, 8, C]
+            for i in range(3):
+                T.variables[f"cp_hidden_{i}_weight"] = rng.standard_normal((E, sizes[i], sizes[i + 1])) * 0.1
+                T.variables[f"cp_hidden_{i}_bias"] = np.zeros((E, 1, sizes[i + 1]))
+            T.variables["cp_output_weight"], T.variables["cp_output_bias"] = rng.standard_normal((E, 8, C)) * 0.1, np.zeros((E, 1, C))
+            z, o = (lambda *sh: np.zeros(sh)), (lambda *sh: np.ones(sh))
+            n, B = 50, 2
+            if context:
+                T.placeholders = [z(m, D), z(m, D), z(m, A), z(m, D * K), z(m, A * K),
+                                  z(E, B, D), z(E, B, D), z(E, B, A), z(E, B, D), z(E, B, D), z(E, B, D * K), z(E, B, A * K),
+                                  z(P), o(P), z(A), o(A), z(D), o(D), z(D * K), o(D * K), z(A * K), o(A * K), z(D), o(D),
+                                  z(m, h, A), o(m, h, A)]
+            else:
+                T.placeholders = [z(m, D), z(m, A), z(m, D), z(E, B, D), z(E, B, A), z(E, B, D),
+                                  z(P), o(P), z(A), o(A), z(D), o(D), z(m, h, A), o(m, h, A)]
+            if use_cem:
+                T.truncated = [None] * ITERS
+                T.normal = [None] * (1 + ITERS * h)
+            else:
+                T.uniform = [ph.gen_discrete_actions(1, m, n, h, A) if x["discrete"] else ph.gen_uniform_actions(1, m, n, h, A).astype(f8)]
+                T.normal = [None] * (1 + h)
+            kw = dict(hidden_sizes=(H, H), hidden_nonlinearity="swish", optimizer=_Optimizer, n_forwards=h, n_candidates=n,
+                      ensemble_size=E, n_particles=E, use_cem=use_cem, normalize_input=spec["normalize_input"], weight_decays=(0.,) * 3)
+            if context:
+                kw.update(cp_hidden_sizes=(8, 8, 8), context_weight_decays=(0.,) * 4, context_out_dim=C, history_length=K,
+                          future_length=1, state_diff=spec["state_diff"], back_coeff=0.0)
+            model = (CaDMModel if context else PETSModel)("dm", env, **kw)
+            assert not T.placeholders
+            model.normalization = OrderedDict(x["normalization"]) if spec["normalize_input"] else None
+            sess = _ActionSession(model, x["cem_answer"] if use_cem else x["rs_answer"])
+            tf.compat.v1.get_default_session = lambda sess=sess: sess
+            hist = (x["cp_obs"], x["cp_act"]) if context else ()
+            warm = (x["init_mean"], x["init_var"]) if use_cem else ()
+            action = model.get_action(x["obs"], *hist, *warm)
+            tag = f"{name}/{'cem' if use_cem else 'rs'}"
+            out[f"{tag}/action"] = np.asarray(action)
+            assert len(sess.feeds) == 1
+            for k, v in sess.feeds[0].items():
+                out[f"{tag}/feed_{k}"] = v
+    return out
+
+
 def main():
     tf = shim.install(np.float64)
     sys.path.insert(0, "/root/reference")
@@ -447,6 +537,9 @@ def main():
     for k, v in run_train_forward(U, tf).items():
         blob[f"train_forward/{k}"] = v
     print("train_forward:", {k: v.shape for k, v in blob.items() if k.startswith("train_forward/")})
+    for k, v in run_get_action(tf).items():
+        blob[f"get_action/{k}"] = v
+    print("get_action:", sorted({k.split("/feed_")[0] for k in blob if k.startswith("get_action/") and "/feed_" in k}))
     replay = run_fit_replay(tf)
     for k, v in replay.items():
         blob[f"fit_replay/{k}"] = v

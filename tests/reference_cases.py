@@ -109,3 +109,28 @@ def make_fit_data(seed=41):
     future_bool = np.ones((n, F))
     future_bool[rng.random(n) < 0.3, 1:] = 0.0          # paths that end before the second future step
     return dict(obs=obs, act=act, obs_next=obs_next, cp_obs=cp_obs, cp_act=cp_act, future_bool=future_bool)
+
+
+GET_ACTION_CASES = dict(
+    cadm_norm=dict(kind="cadm", envname="halfcheetah", normalize_input=True, state_diff=False),
+    cadm_state_diff=dict(kind="cadm", envname="halfcheetah", normalize_input=True, state_diff=True),
+    cadm_raw=dict(kind="cadm", envname="halfcheetah", normalize_input=False, state_diff=False),
+    pets_norm=dict(kind="pets", envname="halfcheetah", normalize_input=True),
+    pets_raw=dict(kind="pets", envname="halfcheetah", normalize_input=False),
+    pets_discrete=dict(kind="pets", envname="cartpole", normalize_input=True),
+)
+
+
+def get_action_inputs(name, spec):
+    """Statistics, observations, histories and the scripted planner answer of one get_action case (shared with the test)."""
+    env = get_env(spec["envname"])
+    D, A, P, K, h, m = env.obs_dim, env.act_dim, env.proc_obs_dim, 3, 4, 2
+    rng = np.random.default_rng(sum(map(ord, name)))
+    pair = lambda n: (rng.standard_normal(n) * 0.1, rng.uniform(0.5, 1.5, n))
+    normalization = dict(obs=pair(P), delta=pair(D), act=pair(A), cp_obs=pair(D * K), cp_act=pair(A * K), back_delta=pair(D))
+    discrete = spec["envname"] == "cartpole"
+    return dict(D=D, A=A, P=P, K=K, h=h, m=m, discrete=discrete, normalization=normalization,
+                obs=rng.standard_normal((m, D)), cp_obs=rng.standard_normal((m, D * K)), cp_act=rng.standard_normal((m, A * K)),
+                init_mean=rng.standard_normal((m, h, A)) * 0.3, init_var=np.full((m, h, A), 0.25),
+                cem_answer=rng.standard_normal((m, h, A)) * 2.0,               # beyond [-1, 1]: the clip must show
+                rs_answer=rng.integers(0, A, size=m) if discrete else rng.standard_normal((m, A)) * 2.0)

@@ -350,3 +350,67 @@ def test_fit_loop_feeds_what_the_reference_fit_feeds(tag, monkeypatch):
     if tag == "cadm":                                                              # the ragged future masks removed rows
         n_rows = sum(b[0].shape[1] for k, b in _RecordingTrainer.calls[:4] if k == "train")
         assert n_rows < int(0.8 * c["n"]) * c["F"] + 1
+
+
+class _FakeEngine:
+    """Records what the host model hands to the native boundary; answers like the library would (the CEM entry point clips
+    inside the C call, cadm_plan_cem_host; random shooting returns the raw first action)."""
+
+    def __init__(self, cem_answer, rs_answer):
+        self.cem_answer, self.rs_answer, self.norm, self.cem_args, self.rs_args = cem_answer, rs_answer, None, None, None
+
+    def set_norm(self, *stats):
+        self.norm = [np.asarray(s, np.float64) for s in stats]
+
+    def plan_cem_host(self, obs, init_mean, init_var, cp_obs=None, cp_act=None, seed=0):
+        self.cem_args = dict(obs=obs, cem_init_mean=init_mean, cem_init_var=init_var, cp_obs=cp_obs, cp_act=cp_act)
+        return np.clip(self.cem_answer, -1, 1).astype(np.float32)
+
+    def plan_rs(self, obs, cp_obs=None, cp_act=None, seed=0):
+        import torch
+        self.rs_args = dict(obs=obs, cp_obs=cp_obs, cp_act=cp_act)
+        return dict(action=torch.as_tensor(np.asarray(self.rs_answer)))
+
+
+@pytest.mark.parametrize("name", ["cadm_norm", "cadm_state_diff", "cadm_raw", "pets_norm", "pets_raw", "pets_discrete"])
+def test_get_action_hands_the_planner_what_the_reference_get_action_feeds(name):
+    """get_action() of the UNMODIFIED reference model classes was run with its session replaced by a recorder.
+    The host mirrors, with a recording engine in place of the library, must hand over the same observation / history / warm
+    start, the same normalisation vectors in the same slots (zeros / ones when normalize_input is off, for the observation
+    history under state_diff, for discrete actions), and return the same action: clipped to [-1, 1] for continuous actions,
+    untouched for discrete ones."""
+    from collections import OrderedDict
+    from test_training import _CpuCadmModel, _CpuModel
+    from cadm_b200.dynamics.core import PlannerModelBase
+    from reference_cases import GET_ACTION_CASES, get_action_inputs
+    spec = GET_ACTION_CASES[name]
+    x = get_action_inputs(name, spec)
+    context = spec["kind"] == "cadm"
+    stat_names = ["obs_mean", "obs_std", "act_mean", "act_std", "delta_mean", "delta_std"] + \
+        (["cp_obs_mean", "cp_obs_std", "cp_act_mean", "cp_act_std"] if context else [])
+    for mode in (["rs"] if x["discrete"] else ["cem", "rs"]):
+        rec = lambda k: REF_CASES[f"get_action/{name}/{mode}/{k}"]
+        model = (_CpuCadmModel(spec["envname"], E=2, H=8, K=x["K"], F=1, C=4) if context else _CpuModel(spec["envname"], E=2, H=8))
+        model.use_cem, model.n_forwards, model._seed, model._calls = mode == "cem", x["h"], 0, 0
+        model.normalize_input, model.discrete = spec["normalize_input"], x["discrete"]
+        if context:
+            model.state_diff = spec["state_diff"]
+        model.engine = _FakeEngine(x["cem_answer"], x["rs_answer"])
+        model.normalization = OrderedDict(x["normalization"]) if spec["normalize_input"] else None
+        PlannerModelBase._push_norm(model)                               # what set_normalization / load / fit do
+        assert len(model.engine.norm) == len(stat_names)
+        for k, got in zip(stat_names, model.engine.norm):
+            assert np.array_equal(got, rec(f"feed_norm_{k}")), (name, mode, k)
+        hist = (x["cp_obs"], x["cp_act"]) if context else ()
+        warm = (x["init_mean"], x["init_var"]) if mode == "cem" else ()
+        action = model.get_action(x["obs"], *hist, *warm)
+        fed = model.engine.cem_args if mode == "cem" else model.engine.rs_args
+        want_keys = ["obs"] + (["cp_obs", "cp_act"] if context else []) + (["cem_init_mean", "cem_init_var"] if mode == "cem" else [])
+        for k in want_keys:
+            assert np.array_equal(np.asarray(fed[k], np.float32), rec(f"feed_{k}").astype(np.float32)), (name, mode, k)
+        want = rec("action")
+        assert action.shape == want.shape
+        if x["discrete"]:
+            assert np.array_equal(action, want) and np.array_equal(want, x["rs_answer"])      # no clip
+        else:
+            assert np.max(np.abs(action - want)) < 1e-6 and np.abs(want).max() == 1.0          # the clip was active
