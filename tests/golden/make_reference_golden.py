@@ -499,6 +499,77 @@ def run_get_action(tf):
     return out
 
 
+class _ParamSession:
+    """The session inside save(): `self.params` is the list the stand-in's trainable_variables() returned (scoped names in
+    creation order); running it yields the injected values."""
+
+    def __init__(self, values):
+        self.values = values
+
+    def run(self, fetches, feed_dict=None):
+        return [np.asarray(self.values[name], np.float32) for name in fetches]
+
+
+def run_checkpoint(tf, dst_dir):
+    """save() of the UNMODIFIED CaDM model class (mlp_cadm_ensemble_cem_dynamics.py:571-577) with a backward model: writes
+    tests/golden/recorded/reference_checkpoint.joblib (+ _norm_stats) through the reference's own code, and returns the
+    value of every variable by scoped name so that the test can tell which array must land in which slot after load()."""
+    from cadm.dynamics.mlp_cadm_ensemble_cem_dynamics import MLPEnsembleCEMDynamicsModel as CaDMModel
+    import types
+    from collections import OrderedDict
+    f8 = np.float64
+    T = shim.TAPE
+    T.__init__()
+    T.dtype = tf.float32 = f8
+    env = reference_env("halfcheetah")
+    D, A, P, K, C, E, H, m, h, n, B = 18, 6, 18, 3, 4, 2, 8, 1, 1, 2, 2
+    env.observation_space = types.SimpleNamespace(shape=(D,))
+    env.action_space = types.SimpleNamespace(shape=(A,))
+    env.proc_observation_space_dims = P
+    rng = np.random.default_rng(123)
+    In = P + A + C
+    for scope in ("ff_model", "backward_model"):
+        for i, (a, b) in enumerate(((In, H), (H, H))):
+            T.variables[f"{scope}/hidden_{i}_weight"] = rng.standard_normal((E, a, b))
+            T.variables[f"{scope}/hidden_{i}_bias"] = rng.standard_normal((E, 1, b))
+        for head in ("mu", "logvar"):
+            T.variables[f"{scope}/output_{head}_weight"] = rng.standard_normal((E, H, D))
+            T.variables[f"{scope}/output_{head}_bias"] = rng.standard_normal((E, 1, D))
+        for nm in ("max_log_var", "max_logvar", "min_log_var", "min_logvar"):
+            T.variables[f"{scope}/{nm}"] = rng.standard_normal((1, D))
+    sizes = [(D + A) * K, 8, 8, 8, C]
+    for i in range(3):
+        T.variables[f"cp_hidden_{i}_weight"] = rng.standard_normal((E, sizes[i], sizes[i + 1]))
+        T.variables[f"cp_hidden_{i}_bias"] = rng.standard_normal((E, 1, sizes[i + 1]))
+    T.variables["cp_output_weight"], T.variables["cp_output_bias"] = rng.standard_normal((E, 8, C)), rng.standard_normal((E, 1, C))
+    z, o = (lambda *sh: np.zeros(sh)), (lambda *sh: np.ones(sh))
+    T.placeholders = [z(m, D), z(m, D), z(m, A), z(m, D * K), z(m, A * K),
+                      z(E, B, D), z(E, B, D), z(E, B, A), z(E, B, D), z(E, B, D), z(E, B, D * K), z(E, B, A * K),
+                      z(P), o(P), z(A), o(A), z(D), o(D), z(D * K), o(D * K), z(A * K), o(A * K), z(D), o(D), z(m, h, A), o(m, h, A)]
+    T.uniform = [ph.gen_uniform_actions(1, m, n, h, A).astype(f8)]
+    T.normal = [None] * (1 + h)
+    model = CaDMModel("dm", env, hidden_sizes=(H, H), hidden_nonlinearity="swish", optimizer=_Optimizer, n_forwards=h,
+                      n_candidates=n, ensemble_size=E, n_particles=E, use_cem=False, weight_decays=(0.,) * 3,
+                      cp_hidden_sizes=(8, 8, 8), context_weight_decays=(0.,) * 4, context_out_dim=C, history_length=K,
+                      future_length=1, state_diff=False, back_coeff=0.5)
+    # value of every variable under the scoped name the constructor created it with
+    values = {}
+    for scoped in model.params:
+        parts = scoped.split("/")
+        keys = [f"{sc}/{parts[-1]}" for sc in reversed(parts[:-1]) if f"{sc}/{parts[-1]}" in T.variables] + [parts[-1]]
+        values[scoped] = T.variables[keys[0]]
+    pair = lambda k: (rng.standard_normal(k), rng.uniform(0.5, 1.5, k))
+    model.normalization = OrderedDict(obs=pair(P), delta=pair(D), act=pair(A), cp_obs=pair(D * K), cp_act=pair(A * K),
+                                      back_delta=pair(D))
+    tf.compat.v1.get_default_session = lambda: _ParamSession(values)
+    path = os.path.join(dst_dir, "reference_checkpoint.joblib")
+    model.save(path)
+    out = {f"var{idx:02d}:{scoped}": np.asarray(values[scoped], np.float32) for idx, scoped in enumerate(model.params)}
+    for k, (mu, sd) in model.normalization.items():
+        out[f"norm/{k}/mean"], out[f"norm/{k}/std"] = mu, sd
+    return out
+
+
 def main():
     tf = shim.install(np.float64)
     sys.path.insert(0, "/root/reference")
@@ -537,6 +608,9 @@ def main():
     for k, v in run_train_forward(U, tf).items():
         blob[f"train_forward/{k}"] = v
     print("train_forward:", {k: v.shape for k, v in blob.items() if k.startswith("train_forward/")})
+    for k, v in run_checkpoint(tf, os.path.join(HERE, "recorded")).items():
+        blob[f"checkpoint/{k}"] = v
+    print("checkpoint:", [k.split(":", 1)[1] for k in sorted(blob) if k.startswith("checkpoint/var")][:4], "...")
     for k, v in run_get_action(tf).items():
         blob[f"get_action/{k}"] = v
     print("get_action:", sorted({k.split("/feed_")[0] for k in blob if k.startswith("get_action/") and "/feed_" in k}))

@@ -414,3 +414,57 @@ def test_get_action_hands_the_planner_what_the_reference_get_action_feeds(name):
             assert np.array_equal(action, want) and np.array_equal(want, x["rs_answer"])      # no clip
         else:
             assert np.max(np.abs(action - want)) < 1e-6 and np.abs(want).max() == 1.0          # the clip was active
+
+
+def test_load_reads_a_checkpoint_written_by_the_reference_save():
+    """SURVEY 8(f) rank 1.  tests/golden/recorded/reference_checkpoint.joblib (+ _norm_stats) was written by save() of the
+    UNMODIFIED CaDM model class with a backward model (mlp_cadm_ensemble_cem_dynamics.py:571-577).  load() of the host mirror
+    must put every array into the slot the reference created it in -- encoder, forward model, backward model, each with its
+    own logvar bounds -- and a model built without a backward model must accept the same file and ignore the tail."""
+    from test_training import _CpuCadmModel
+    path = os.path.join(HERE, "golden", "recorded", "reference_checkpoint.joblib")
+    ref = {k.split("/", 1)[1]: REF_CASES[k] for k in REF_CASES.files if k.startswith("checkpoint/var")}
+    by_name = {k.split(":", 1)[1]: v for k, v in ref.items()}
+    order = [k.split(":", 1)[1] for k in sorted(ref)]
+    assert len(order) == 8 + 2 * (4 + 4 + 2)                          # encoder 4 x (W, b); each MLP: 2 x (W, b), heads, bounds
+    pick = lambda scope, name: next(v for k, v in by_name.items() if f"/{scope}/" in k and k.endswith("/" + name))
+
+    def check_mlp(d, scope):
+        for i in range(2):
+            assert np.array_equal(d["W"][i], pick(scope, f"hidden_{i}_weight")) and np.array_equal(d["b"][i], pick(scope, f"hidden_{i}_bias"))
+        assert np.array_equal(d["W_mu"], pick(scope, "output_mu_weight")) and np.array_equal(d["b_mu"], pick(scope, "output_mu_bias"))
+        assert np.array_equal(d["W_lv"], pick(scope, "output_logvar_weight")) and np.array_equal(d["b_lv"], pick(scope, "output_logvar_bias"))
+        mx = [v for k, v in by_name.items() if f"/{scope}/" in k and k.rsplit("/", 1)[1] in ("max_logvar", "max_log_var")]
+        mn = [v for k, v in by_name.items() if f"/{scope}/" in k and k.rsplit("/", 1)[1] in ("min_logvar", "min_log_var")]
+        assert len(mx) == 1 and len(mn) == 1
+        assert np.array_equal(d["max_logvar"], mx[0]) and np.array_equal(d["min_logvar"], mn[0])
+
+    for back_coeff in (0.5, 0.0):
+        model = _CpuCadmModel("halfcheetah", E=2, H=8, n_hidden=2, K=3, F=1, C=4, cp_hidden=(8, 8, 8), back_coeff=back_coeff)
+        model.load(path)
+        assert model.pushed == 1
+        for i in range(3):
+            assert np.array_equal(model._enc["W"][i], pick("context_model", f"cp_hidden_{i}_weight"))
+            assert np.array_equal(model._enc["b"][i], pick("context_model", f"cp_hidden_{i}_bias"))
+        assert np.array_equal(model._enc["W"][3], pick("context_model", "cp_output_weight"))
+        assert np.array_equal(model._enc["b"][3], pick("context_model", "cp_output_bias"))
+        check_mlp(model._dyn, "ff_model")
+        if back_coeff > 0:
+            check_mlp(model._back, "backward_model")
+            assert not np.array_equal(model._back["max_logvar"], model._dyn["max_logvar"])       # distinct values per scope
+        else:
+            assert model._back is None
+        assert list(model.normalization) == ["obs", "delta", "act", "cp_obs", "cp_act", "back_delta"]
+        for k, (mu, sd) in model.normalization.items():
+            assert np.array_equal(mu, REF_CASES[f"checkpoint/norm/{k}/mean"]) and np.array_equal(sd, REF_CASES[f"checkpoint/norm/{k}/std"])
+    # and the way back: what save() of the mirror writes is, array for array, what the reference wrote
+    import joblib
+    import tempfile
+    model = _CpuCadmModel("halfcheetah", E=2, H=8, n_hidden=2, K=3, F=1, C=4, cp_hidden=(8, 8, 8), back_coeff=0.5)
+    model.load(path)
+    with tempfile.TemporaryDirectory() as tmp:
+        model.save(os.path.join(tmp, "ck"))
+        ours, theirs = joblib.load(os.path.join(tmp, "ck")), joblib.load(path)
+        assert len(ours) == len(theirs) and all(np.array_equal(a, b) and a.shape == b.shape for a, b in zip(ours, theirs))
+        n_ours, n_theirs = joblib.load(os.path.join(tmp, "ck_norm_stats")), joblib.load(path + "_norm_stats")
+        assert list(n_ours) == list(n_theirs) and all(np.array_equal(n_ours[k][j], n_theirs[k][j]) for k in n_ours for j in (0, 1))
