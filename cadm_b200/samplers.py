@@ -19,7 +19,7 @@ The arithmetic is the engine's own `cadm_plan_cem`; `tests/test_gpu_envs.py::tes
 the actions equal the host-side loop's bit for bit.
 
 The callers and data formats either side of the planner live here too, as host code with the reference's
-interfaces: `Sampler` (sampler.py: the rollout loop that owns the state above and records paths -- it plans through a
+interfaces: `BaseSampler` (base.py: the single-environment loop), `Sampler` (sampler.py: the rollout loop that owns the state above and records paths -- it plans through a
 `PlannerSession` when the policy's dynamics model has an engine, and through `policy.get_actions` with NumPy state
 otherwise), `IterativeEnvExecutor` (vectorized_env_executor.py:7-69), `rollout_multi` / `context_rollout_multi`
 (samplers/utils.py: the trainer's evaluation rollouts, same state) and `ModelSampleProcessor`
@@ -213,6 +213,50 @@ def _stack_dicts(dicts):
         vals = [d[k] for d in dicts]
         out[k] = _stack_dicts(vals) if isinstance(vals[0], dict) else np.asarray(vals)
     return out
+
+
+class BaseSampler:
+    """cadm/samplers/base.py:9-112 -- the single-environment sampler: one environment, `policy.get_action(obs)` once per
+    step (no warm start, no history: it serves random-shooting policies and random exploration), paths cut at `done` or
+    after `max_path_length` steps, until num_rollouts * max_path_length steps of FINISHED paths are collected."""
+
+    def __init__(self, env, policy, num_rollouts, max_path_length):
+        assert hasattr(env, 'reset') and hasattr(env, 'step')
+        self.env, self.policy, self.max_path_length = env, policy, max_path_length
+        self.total_samples = num_rollouts * max_path_length
+        self.total_timesteps_sampled = 0
+
+    def _act(self, obs, random):
+        if random:
+            return self.env.action_space.sample(), {}
+        action, info = self.policy.get_action(obs)
+        return (action[0] if action.ndim == 2 else action), info
+
+    def obtain_samples(self, log=False, log_prefix='', random=False):
+        paths, collected = [], 0
+        keys = ("observations", "actions", "rewards", "dones", "env_infos", "agent_infos")
+        running = {k: [] for k in keys}
+        obs, steps = np.asarray(self.env.reset()), 0
+        while collected < self.total_samples:
+            action, agent_info = self._act(obs, random)
+            next_obs, reward, done, env_info = self.env.step(action)
+            steps += 1
+            done = done or steps >= self.max_path_length
+            if done:                                         # the stored transition keeps the pre-reset observation only
+                next_obs, steps = self.env.reset(), 0
+            if isinstance(reward, np.ndarray):
+                reward = reward[0]
+            for k, v in zip(keys, (obs, action, reward, done, env_info, agent_info)):
+                running[k].append(v)
+            if done:
+                path = {k: np.asarray(running[k]) for k in keys[:4]}
+                path["env_infos"], path["agent_infos"] = _stack_dicts(running["env_infos"]), _stack_dicts(running["agent_infos"])
+                paths.append(path)
+                collected += len(running["rewards"])
+                running = {k: [] for k in keys}
+            obs = next_obs
+        self.total_timesteps_sampled += self.total_samples
+        return paths
 
 
 class Sampler:

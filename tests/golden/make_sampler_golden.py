@@ -22,7 +22,7 @@ sys.dont_write_bytecode = True                              # /root/reference is
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from sampler_fakes import FakeEnv, ScriptedPolicy, controller_dispatch_log          # noqa: E402
+from sampler_fakes import FakeEnv, ScriptedPolicy, ScriptedSinglePolicy, controller_dispatch_log          # noqa: E402
 
 SCENARIOS = dict(
     # name: (context, state_diff, use_cem, history_length, future_length, num_rollouts, max_path_length, horizon)
@@ -120,6 +120,31 @@ def run(Sampler, Processor, name):
     return out
 
 
+BASE_SCENARIOS = dict(base_policy=(False, 3, 6), base_random=(True, 2, 5))       # name: (random, num_rollouts, max_path_length)
+
+
+def run_base(name):
+    """cadm/samplers/base.py BaseSampler.obtain_samples: one environment, policy.get_action per step."""
+    from cadm.samplers.base import BaseSampler
+    random, m, T = BASE_SCENARIOS[name]
+    FakeEnv._copies = 0
+    env = FakeEnv(lengths=((4, 2, 30, 3, 30),))
+    policy = ScriptedSinglePolicy(env.act_dim)
+    sampler = BaseSampler(env, policy, m, T)
+    paths = sampler.obtain_samples(log=False, random=random)
+    out = {"n_calls": np.int64(len(policy.calls)), "n_paths": np.int64(len(paths)),
+           "total_timesteps_sampled": np.int64(sampler.total_timesteps_sampled)}
+    for i, c in enumerate(policy.calls):
+        out[f"call{i}_obs"] = c
+    for i, p in enumerate(paths):
+        for k in ("observations", "actions", "rewards", "dones"):
+            out[f"path{i}_{k}"] = np.array(p[k], copy=True)
+        out[f"path{i}_env_t"] = p["env_infos"]["t"]
+        if not random:
+            out[f"path{i}_agent_s"] = p["agent_infos"]["s"]
+    return out
+
+
 def main():
     Sampler, Processor = import_reference()
     blob = {}
@@ -128,6 +153,9 @@ def main():
             blob[f"{name}/{k}"] = v
     for name in EVAL_SCENARIOS:
         for k, v in run_eval(name).items():
+            blob[f"{name}/{k}"] = v
+    for name in BASE_SCENARIOS:
+        for k, v in run_base(name).items():
             blob[f"{name}/{k}"] = v
     from cadm.policies.mpc_controller import MPCController
     blob["mpc_controller/dispatch"] = np.array(controller_dispatch_log(MPCController))

@@ -82,6 +82,19 @@ class ScriptedPolicy:
         return np.clip(np.sin(s[:, None] + 0.37 * grid[0, 0][None, :]), -1.0, 1.0), []
 
 
+class ScriptedSinglePolicy:
+    """get_action(obs) for the single-environment sampler: closed form of the observation, returned as a [1, A] batch (what
+    MPCController.get_action hands back for one observation); records what it was given."""
+
+    def __init__(self, act_dim):
+        self.act_dim, self.calls = act_dim, []
+
+    def get_action(self, observation):
+        obs = np.asarray(observation, dtype=np.float64)
+        self.calls.append(obs.copy())
+        return np.sin(obs.sum() + 0.37 * np.arange(self.act_dim))[None, :], {"s": np.float64(obs.sum())}
+
+
 class RecordingDynamicsModel:
     """get_action() records which positional arguments it was given (by tag) and returns a constant."""
 

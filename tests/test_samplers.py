@@ -217,3 +217,36 @@ def test_mpc_controller_dispatches_like_the_reference():
     got = controller_dispatch_log(MPCController)
     assert got == str(GOLDEN["mpc_controller/dispatch"])
     assert "('obs', 'cp_obs', 'cp_act', 'mean', 'var')" in got and "('obs', 'mean', 'var')" in got
+
+
+BASE_SCENARIOS = dict(base_policy=(False, 3, 6), base_random=(True, 2, 5))       # the generator's table
+
+
+@pytest.mark.parametrize("name", list(BASE_SCENARIOS))
+def test_single_environment_sampler_matches_the_reference(name):
+    """cadm/samplers/base.py BaseSampler.obtain_samples (the single-environment caller of policy.get_action): what
+    the policy is fed, where paths are cut (done, or max_path_length steps), the [1, A] -> [A] action, the stacked env / agent
+    infos and the sample accounting, against a recording of the unmodified class."""
+    from sampler_fakes import ScriptedSinglePolicy
+    from cadm_b200.samplers import BaseSampler
+    random, m, T = BASE_SCENARIOS[name]
+    g = lambda k: GOLDEN[f"{name}/{k}"]
+    FakeEnv._copies = 0
+    env = FakeEnv(lengths=((4, 2, 30, 3, 30),))
+    policy = ScriptedSinglePolicy(env.act_dim)
+    sampler = BaseSampler(env, policy, m, T)
+    paths = sampler.obtain_samples(log=False, random=random)
+    assert len(policy.calls) == int(g("n_calls")) and len(paths) == int(g("n_paths"))
+    assert sampler.total_timesteps_sampled == int(g("total_timesteps_sampled")) == m * T
+    for i, obs in enumerate(policy.calls):
+        _same(obs, g(f"call{i}_obs"), i)
+    for i, p in enumerate(paths):
+        for k in ("observations", "actions", "rewards", "dones"):
+            _same(p[k], g(f"path{i}_{k}"), (i, k))
+        _same(p["env_infos"]["t"], g(f"path{i}_env_t"), i)
+        if random:
+            assert p["agent_infos"] == {}
+        else:
+            _same(p["agent_infos"]["s"], g(f"path{i}_agent_s"), i)
+    lengths = [len(p["rewards"]) for p in paths]
+    assert max(lengths) == T and min(lengths) < T                    # both kinds of path end occur
