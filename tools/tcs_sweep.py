@@ -40,7 +40,7 @@ def run(variant, rows, kps, trace=False, skew=0):
             print(f"  step {t}: total {tr[t + 1, 0] - base} cycles")
             print("    epi :", " ".join(f"{n}={tr[t, i] - base}" for i, n in enumerate(names)))
             print("    fin : items_done=%d published=%d bar=%d" % (tr[t, 13] - base, tr[t, 14] - base, tr[t, 15] - base))
-            print("    mma :", " ".join(f"g{g}:first_ready={tr[t, 32 + 4 * g] - base},issued={tr[t, 33 + 4 * g] - base}" for g in range(5)))
+            print("    mma :", " ".join(f"g{g}:first_ready={tr[t, 32 + 4 * g] - base},issued={tr[t, 33 + 4 * g] - base},xr1={tr[t, 34 + 4 * g] - base},t0_commit={tr[t, 35 + 4 * g] - base}" for g in range(5)))
     model.engine.close()
 
 
