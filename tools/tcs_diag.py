@@ -9,7 +9,6 @@ spec = importlib.util.spec_from_file_location("tcs_sweep_mod", "tools/tcs_sweep.
 src = open("tools/tcs_sweep.py").read().split("\nrun(1, 0, 4)")[0]        # the definitions only
 ns = {"__name__": "tcs_diag"}
 exec(compile(src, "tools/tcs_sweep.py", "exec"), ns)
-for name, bits in (("default", 0), ("no side warps", 0x80), ("no noise", 0x100), ("no reward / prefetch", 0x200), ("no side work at all", 0x300),
-                   ("no weight copies", 1), ("no hidden epilogue", 2)):
+for name, bits in (("production kernel (no diagnostics compiled in)", 0), ("no weight copies", 1), ("no hidden epilogue", 2), ("neither", 3)):
     print("==", name, flush=True)
     ns["run"](2, 32, 4, trace=True, skew=bits << 20)
