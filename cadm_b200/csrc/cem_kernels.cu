@@ -140,28 +140,51 @@ __device__ __forceinline__ float elite_action(const RefitParams& R, int mi, int 
 __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
     extern __shared__ unsigned long long keys[];      // [npad] then (optionally) the staged elite rows [K][hA] fp32
     __shared__ int s_el[256];
+    __shared__ unsigned long long s_sel[256];
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_need, s_count;
     const int mi = blockIdx.x;
     const int tid = threadIdx.x;
     const int n = R.n_global;
     const int K = R.k_elites;
     const int hA = R.h * R.A;
     float* el = reinterpret_cast<float*>(keys + R.npad);
-    if (R.peer_flags != nullptr) {
-        // fused all-gather: wait until every rank's slice of this iteration has landed in OUR returns buffer
-        // (bounded: a rank that died must not leave the others spinning on the GPU for ever -- after ~4e9 cycles, about two
-        // seconds, the wait gives up and reports through the host-mapped word; the host raises on the next call)
+    const float* returns_buf = R.returns_buf;
+    if (R.peers != nullptr) {
+        // Fused all-gather over peer memory (multi-GPU): this CTA averages the particle returns of ITS environment's local
+        // candidates (the fixed summation order of core/utils.py:170, so the value does not depend on the sharding), stores
+        // the slice into the returns buffer of EVERY rank (NVLink / NVSwitch stores), publishes the iteration's epoch in flag
+        // (rank, environment) of every rank with system-scope release ordering, and then waits until every rank's slice of
+        // this environment has landed in OUR buffer.  No separate scatter kernel, no collective call, no host round trip.
+        const long long slice = ((long long)R.rank * R.m + mi) * R.n_local;
+        for (int i = tid; i < R.n_local; i += blockDim.x) {
+            const float* r = R.ret_p_local + ((size_t)mi * R.n_local + i) * R.p;
+            float sum = 0.f;
+            for (int q = 0; q < R.p; ++q) sum += r[q];
+            const float v = sum / (float)R.p;
+            for (int g = 0; g < R.world; ++g) reinterpret_cast<float*>(R.peers[g] + R.slice_off)[slice + i] = v;
+        }
+        __threadfence_system();
+        __syncthreads();
         if (tid < R.world) {
+            int* flag = reinterpret_cast<int*>(R.peers[tid] + R.flag_off) + R.rank * R.m_max + mi;
+            asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(R.peer_epoch) : "memory");
+            // bounded wait (a rank that died must not leave the others spinning for ever): gives up after R.timeout_cycles and
+            // reports through the host-mapped word; the host raises on the call that ends this decision
+            const int* mine = reinterpret_cast<const int*>(R.peers[R.rank] + R.flag_off) + tid * R.m_max + mi;
             int seen;
             const long long t0 = clock64();
             do {
-                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(R.peer_flags + tid) : "memory");
-                if (seen - R.peer_epoch < 0 && clock64() - t0 > 4000000000ll) {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+                if (seen - R.peer_epoch < 0 && clock64() - t0 > R.timeout_cycles) {
                     if (R.peer_timeout) *reinterpret_cast<volatile int*>(R.peer_timeout) = 1 + tid;
                     break;
                 }
             } while (seen - R.peer_epoch < 0);
         }
         __syncthreads();
+        returns_buf = reinterpret_cast<const float*>(R.peers[R.rank] + R.slice_off);
     }
     for (int i = tid; i < R.npad; i += blockDim.x) {
         unsigned long long key = ~0ull;
@@ -174,7 +197,7 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
                 v = sum / (float)R.p;
             } else {
                 const int g = i / R.n_local, nl = i - g * R.n_local;
-                v = R.returns_buf[((size_t)g * R.m + mi) * R.n_local + nl];
+                v = returns_buf[((size_t)g * R.m + mi) * R.n_local + nl];
             }
             if (R.returns_log) R.returns_log[(size_t)mi * n + i] = v;
             key = elite_key(v, i);
@@ -184,7 +207,7 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
     __syncthreads();
     if (n <= 256 && !R.mode_rs) {
         // rank by counting: keys are distinct (the index is part of the key), so rank = #smaller keys.  O(n^2 / 32) broadcast
-        // loads: 1.4k for n = 200, but 20k (10 us) for n = 800 -- above 256 candidates the bitonic sort below is faster
+        // loads: 1.4k for n = 200
         if (tid < n) {
             const unsigned long long mine = keys[tid];
             int rank = 0;
@@ -193,24 +216,63 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
             if (rank < K) s_el[rank] = tid;
         }
     } else {
-        // bitonic sort, ascending
-        for (int size = 2; size <= R.npad; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int i = tid; i < R.npad / 2; i += blockDim.x) {
-                    const int lo = 2 * i - (i & (stride - 1));
-                    const int hi = lo + stride;
-                    const bool up = (lo & size) == 0;
-                    const unsigned long long a = keys[lo], b = keys[hi];
-                    if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
-                }
-                __syncthreads();
+        // Radix select of the K smallest keys (tf.nn.top_k order: larger return first, ties -> lower index first; keys are
+        // distinct, so "the K smallest" is exact): the key's 32 value bits and 16 index bits, most significant byte first, one
+        // 256-bin shared-memory histogram per byte over the keys that match the prefix found so far.  6 passes over n keys
+        // instead of the log^2(n) compare-exchange rounds of a full sort (n = 1600: 66 rounds with a barrier each).
+        if (tid == 0) { s_prefix = 0ull; s_need = (unsigned)K; }
+        __syncthreads();
+        for (int pass = 0; pass < 6; ++pass) {
+            const int shift = pass < 4 ? 56 - 8 * pass : (pass == 4 ? 8 : 0);
+            if (tid < 256) s_hist[tid] = 0u;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            const unsigned long long himask = shift + 8 >= 64 ? 0ull : (~0ull << (shift + 8));
+            for (int i = tid; i < n; i += blockDim.x) {
+                const unsigned long long k = keys[i];
+                if ((k & himask) == (prefix & himask)) atomicAdd(&s_hist[(unsigned)(k >> shift) & 255u], 1u);
             }
+            __syncthreads();
+            if (tid < 32) {
+                // warp 0: the digit at which the running count reaches `need` (8 bins per lane, then a warp scan)
+                unsigned loc[8], sum = 0u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { loc[q] = s_hist[tid * 8 + q]; sum += loc[q]; }
+                unsigned incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned up = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += up; }
+                const unsigned excl = incl - sum, need = s_need;
+                if (excl < need && need <= incl) {            // exactly one lane
+                    unsigned run = excl;
+                    int d = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { if (run < need && need <= run + loc[q]) { d = q; break; } run += loc[q]; }
+                    s_prefix = prefix | ((unsigned long long)(tid * 8 + d) << shift);
+                    s_need = need - run;
+                }
+            }
+            __syncthreads();
+        }
+        // s_prefix is now the K-th smallest key (bits 16..31 of a key are zero: indices are below 2^14): gather what is <= it
+        if (tid == 0) s_count = 0u;
+        __syncthreads();
+        const unsigned long long kth = s_prefix;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const unsigned long long k = keys[i];
+            if (k <= kth) { const unsigned pos = atomicAdd(&s_count, 1u); if (pos < 256u) s_sel[pos] = k; }
+        }
+        __syncthreads();
+        if (tid < K) {                                        // order the K selected keys by counting
+            const unsigned long long mine = s_sel[tid];
+            int rank = 0;
+            for (int jx = 0; jx < K; ++jx) rank += s_sel[jx] < mine ? 1 : 0;
+            s_el[rank] = (int)(mine & 0xffffffffu);
         }
         if (R.mode_rs) {
-            if (tid == 0) R.best[mi] = (int)(keys[0] & 0xffffffffu);
+            __syncthreads();
+            if (tid == 0) R.best[mi] = s_el[0];
             return;
         }
-        for (int i = tid; i < K; i += blockDim.x) s_el[i] = (int)(keys[i] & 0xffffffffu);
     }
     __syncthreads();
     for (int i = tid; i < K; i += blockDim.x)

@@ -33,8 +33,15 @@ struct RefitParams {
     const float* ret_p;             // nullable: [m, n_global, p] particle returns (world == 1: particle mean folded in)
     int p;
     int stage_elites;               // set by the launcher: elite rows fit in shared memory
-    const int* peer_flags;          // nullable: [world] arrival epochs written by the peers (fused peer-memory all-gather)
-    int peer_epoch;                 // wait until every peer_flags[r] >= peer_epoch before reading returns_buf
+    // fused peer-memory all-gather (multi-GPU; nullable): the refit kernel itself averages this rank's particle returns,
+    // stores the slice into every rank's exchange block and waits for the other ranks' slices (cem_kernels.cu)
+    unsigned char* const* peers;    // device array [world]: base of every rank's exchange block as seen from this device
+    long long slice_off;            // byte offset of this epoch parity's returns buffer [world, m, n_local] inside a block
+    long long flag_off;             // byte offset of this epoch parity's flags [world, m_max] inside a block
+    const float* ret_p_local;       // this rank's particle returns [m, n_local, p]
+    int rank, m_max;
+    int peer_epoch;                 // wait until flag (r, env) >= peer_epoch for every rank r
+    long long timeout_cycles;       // bound of that wait (clock64 cycles)
     int* peer_timeout;              // host-mapped word set to 1 + rank-waited-for when the wait gives up (a peer died)
     // random shooting (mode_rs): argmax only
     int mode_rs;
@@ -56,11 +63,6 @@ struct EncoderParams {
 
 cudaError_t launch_sample_actions(const SampleParams& S, cudaStream_t stream);
 cudaError_t launch_particle_mean(const float* ret_p, float* out, int count, int p, cudaStream_t stream);
-// particle mean + all-gather in one kernel: every rank writes its [count] slice straight into the returns buffer of EVERY
-// rank (peer memory over NVLink) and then publishes `epoch` in flag `rank` of every rank.
-//   peers[r] = base of rank r's exchange block; slice_off / flag_off = byte offsets of this rank's slice / flag in a block
-cudaError_t launch_particle_mean_scatter(const float* ret_p, int count, int p, unsigned char* const* peers, int world,
-                                         long long slice_off, long long flag_off, int epoch, int* block_counter, cudaStream_t stream);
 cudaError_t launch_refit(RefitParams R, cudaStream_t stream);
 cudaError_t launch_rs_gather(const float* actions, const int* actions_int, const int* best, int m, int n_local, int h,
                              int A, float* action, int* action_int, cudaStream_t stream);

@@ -1001,6 +1001,8 @@ cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long 
     if (T.Np > 256 || T.NHp > 128 || kps < 1 || kps > kSMaxKps) return cudaErrorInvalidConfiguration;
     int N = rows_override > 0 ? rows_override : tcs_pick_rows(P.rows_per_member, P.E, num_sms);
     N = min(kSMaxRows, max(16, round_up(N, 16)));
+    // wide state vectors with 64-row tiles do not leave room for two weight stages: take narrower tiles (more of them)
+    while (N > 16 && tcs_smem_layout(N, P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, T.Kcap, T.nkb0, kps, 2).total > 226 * 1024) N -= 16;
     int tiles = (P.rows_per_member + N - 1) / N;
     N = min(N, round_up((P.rows_per_member + tiles - 1) / tiles, 16));      // balance the rows over the tiles
     P.rows_per_cta = min(N, (P.rows_per_member + tiles - 1) / tiles);
