@@ -8,8 +8,12 @@ dynamics MLP, then top-k + refit) on synthetic start states and random-init weig
 iters * m * n * p * h (candidate x particle x horizon-step dynamics evaluations).
 
 N = 1   workload = BASELINE.json configs[1]: HalfCheetah PE-TS (ens=5, part=20, cand=200, horizon=30), m = 1.
-N > 1   one process per GPU (torchrun); candidates are sharded, 200 per GPU (weak scaling: n = 200 N), one NCCL
-        all-gather of the per-candidate returns per CEM iteration.
+N > 1   one process per GPU (torchrun); candidates are sharded with one exchange of the per-candidate returns per CEM
+        iteration (fused into the refit kernel over peer memory; NCCL all-gather as the fallback).  `--scaling weak`
+        (default): 200 candidates per GPU (n = 200 N) is the line's `value`; `--scaling strong`: the NAMED config
+        (n = 200) split over the N GPUs.  Either way the line carries the other leg, BASELINE configs[3] (Ant + CaDM,
+        n = 1000) split over the N GPUs, and the environment-sharded leg (10 environments per GPU, no exchange) under
+        `legs`, so that one driver run per N records all of them.
 
 value   device-resident: inputs already in HBM, CUDA-event time of K decisions (L2 flushed between decisions).
 e2e     the same decisions through DynamicsModel.get_action() with HOST (NumPy) buffers: H2D of the inputs and
@@ -31,7 +35,6 @@ sys.path.insert(0, ROOT)
 
 METRIC = "CEM actions/sec (cand x part x horizon steps/s)"
 UNIT = "actions/s"
-CAND_PER_GPU = 200
 
 
 def load_peaks():
@@ -121,7 +124,10 @@ def run_reference(args, rank, world):
     from cadm_b200.synth import CONFIGS, WORKLOAD_NAMES, synthetic_inputs
     from oracle.envs import get_env
     cfg = dict(CONFIGS[args.config])
-    n = CAND_PER_GPU * world if args.config == "C2" else cfg["candidates"]
+    base_n = args.cand or cfg["candidates"]
+    n = base_n if (world == 1 or args.scaling == "strong" or args.cand) else base_n * world      # the engine arm's primary leg
+    if args.part:
+        cfg["particles"] = args.part
     env = get_env(cfg["env"])
     threads = os.cpu_count()
     torch.set_num_threads(threads)
@@ -157,7 +163,8 @@ def run_reference(args, rank, world):
     sample = f"{args.steps} x ({iters} of 5 CEM iterations of one decision, m={m}, n={n})"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if (world == 1 or args.scaling == "strong" or args.cand) else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAMES[args.config] + f", m={m}, n={n}",
                    "note": "CPU restatement of the TF1.15 graph (TF not installable here), PyTorch-CPU fp32, "
@@ -202,38 +209,34 @@ def cpu_baseline_leg(args, model, env, cfg, budget_s=20.0):
 
 
 # --------------------------------------------------------------------------------------------------------
-def run_engine(args, rank, world, local_rank):
+def measure_leg(args, rank, world, local_rank, config, m, n_total, particles, sharding, flush, timed_e2e=False, sampler=None):
+    """One workload on `world` ranks: build the model, warm up, time args.steps decisions with CUDA events (L2 flushed between
+    them, outside the events), max over ranks.  sharding: "candidates" (n_total split over the ranks, one exchange per CEM
+    iteration) or "envs" (every rank plans its own m environments with all n_total candidates, no exchange at all)."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    from cadm_b200.parallel import ShardedCEMPlanner
-    from cadm_b200.synth import WORKLOAD_NAMES, build_model, flops_per_unit, synthetic_inputs
+    from cadm_b200.synth import build_model, flops_per_unit, synthetic_inputs
 
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    n_total = CAND_PER_GPU * world if args.config == "C2" else None
-    if args.cand:
-        n_total = args.cand                       # C5 sweep cell: global candidate count as given (strong scaling over GPUs)
-    model, env, cfg = build_model(args.config, m_max=max(args.m, 1), candidates=n_total, particles=args.part or None, rank=rank,
-                                  world=world, precision=args.precision, device=dev)
-    if n_total is None:
-        n_total = cfg["candidates"]
+    by_env = sharding == "envs"
+    model, env, cfg = build_model(config, m_max=max(m, 1), candidates=n_total, particles=particles or None,
+                                  rank=0 if by_env else rank, world=1 if by_env else world, precision=args.precision, device=dev)
     eng = model.engine
-    m, h, p, E = args.m, cfg["horizon"], cfg["particles"], cfg["ensemble"]
-    inp = synthetic_inputs(env, m, h, cfg["context"], seed=0)
+    if by_env:
+        eng.set_option("env_offset", rank * m)            # this rank's block of the m * world environments of the decision
+    h, p, E = cfg["horizon"], cfg["particles"], cfg["ensemble"]
+    inp = synthetic_inputs(env, m, h, cfg["context"], seed=rank if by_env else 0)
     dv = {k: torch.from_numpy(v).to(dev) for k, v in inp.items()}
-    planner = ShardedCEMPlanner(eng)
-    units = 5 * m * n_total * p * h
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
-
-    out_mean = torch.empty_like(dv["init_mean"])
-    out_var = torch.empty_like(dv["init_var"])
+    planner = None if (by_env or world == 1) else model.sharded_planner()
+    units = 5 * m * n_total * p * h * (world if by_env else 1)
+    out_mean, out_var = torch.empty_like(dv["init_mean"]), torch.empty_like(dv["init_var"])
 
     def step(i, timed=None):
         seed = (1 << 32) | i
         if timed is not None:
             timed[0].record()
-        if world == 1:
+        if planner is None or planner.fused:
             eng.plan_cem_into(dv["obs"], dv["init_mean"], dv["init_var"], out_mean, out_var, dv.get("cp_obs"), dv.get("cp_act"), seed=seed)
         else:
             planner.plan(dv["obs"], dv["init_mean"], dv["init_var"], dv.get("cp_obs"), dv.get("cp_act"), seed=seed, logs=False)
@@ -249,10 +252,7 @@ def run_engine(args, rank, world, local_rank):
     for i in range(args.warmup):
         step(i)
     barrier()
-
     eng.set_timing(True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = eng.launch_count
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = []
@@ -272,99 +272,143 @@ def run_engine(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
 
-    # ---- e2e: the public host API (NumPy in / NumPy out), H2D + D2H inside the timed region
+    # ---- e2e: the public host API (NumPy in / NumPy out), H2D + D2H inside the timed region -- DynamicsModel.get_action(), which
+    # at world > 1 drives the candidate-sharded planner (every rank calls it with the same inputs)
     e2e = None
-    if world == 1:
+    if timed_e2e and not by_env:
+        ga = (lambda: model.get_action(inp["obs"], inp["cp_obs"], inp["cp_act"], inp["init_mean"], inp["init_var"])) if cfg["context"] \
+            else (lambda: model.get_action(inp["obs"], inp["init_mean"], inp["init_var"]))
         for i in range(2):
-            model.get_action(inp["obs"], *( (inp["cp_obs"], inp["cp_act"]) if cfg["context"] else ()), inp["init_mean"], inp["init_var"])
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            if cfg["context"]:
-                model.get_action(inp["obs"], inp["cp_obs"], inp["cp_act"], inp["init_mean"], inp["init_var"])
-            else:
-                model.get_action(inp["obs"], inp["init_mean"], inp["init_var"])
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        h2d = 4 * m * (env.obs_dim + 2 * h * env.act_dim + ((env.obs_dim + env.act_dim) * 10 if cfg["context"] else 0))
-        d2h = 4 * m * h * env.act_dim
-        e2e = {"value": units * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": 1e3 * e2e_s / args.steps}
-        # the same control step with the sampler-side state on the device (PlannerSession): only the observation goes up and
-        # the first action comes down; warm start, init_var and the history buffers stay in HBM
-        from cadm_b200.samplers import PlannerSession
-        sess = PlannerSession(model, m, state_diff=True)
-        obs64 = inp["obs"].astype(np.float64)
-        for i in range(2):
-            a = sess.act(obs64)
-            sess.observe(obs64 + 0.01, None)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            a = sess.act(obs64)
-            sess.observe(obs64 + 0.01 * (i + 1), None)
-        torch.cuda.synchronize()
-        sess_s = time.perf_counter() - t0
-        e2e["session"] = {"value": units * args.steps / sess_s, "unit": UNIT, "ms_per_step": 1e3 * sess_s / args.steps,
-                          "h2d_bytes_per_step": 4 * m * env.obs_dim * 2, "d2h_bytes_per_step": 4 * m * env.act_dim,
-                          "what": "PlannerSession.act + observe: warm start / init_var / history buffers resident on the device"}
-    else:
-        # multi-rank: same decision through the sharded planner fed from pinned host tensors
-        pin = {k: torch.from_numpy(v).pin_memory() for k, v in inp.items()}
-        d2 = {k: torch.empty_like(v, device=dev) for k, v in pin.items()}           # staging buffers, allocated once
-        out_host = torch.empty((m, h, env.act_dim), dtype=torch.float32).pin_memory()
+            ga()
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
-            for k, v in pin.items():
-                d2[k].copy_(v, non_blocking=True)                                    # H2D of this step's inputs
-            o = planner.plan(d2["obs"], d2["init_mean"], d2["init_var"], d2.get("cp_obs"), d2.get("cp_act"),
-                             seed=(2 << 32) | i, logs=False)
-            out_host.copy_(o["mean"], non_blocking=True)                             # D2H of the plan
-            torch.cuda.synchronize()
-            out_host.clamp_(-1, 1)                                                   # get_action clip (host side, as the reference)
+            ga()
         barrier()
         e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
         h2d = 4 * m * (env.obs_dim + 2 * h * env.act_dim + ((env.obs_dim + env.act_dim) * 10 if cfg["context"] else 0))
-        e2e = {"value": units * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 4 * m * h * env.act_dim, "ms_per_step": 1e3 * e2e_s / args.steps}
+        e2e = {"value": units * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * m * h * env.act_dim,
+               "ms_per_step": 1e3 * e2e_s / args.steps, "api": "DynamicsModel.get_action (NumPy in / NumPy out)"}
+        if planner is None or planner.fused:
+            # the same control step with the sampler-side state on the device (PlannerSession): only the observation goes up and
+            # the first action comes down; warm start, init_var and the history buffers stay in HBM
+            from cadm_b200.samplers import PlannerSession
+            sess = PlannerSession(model, m, state_diff=True)
+            obs64 = inp["obs"].astype(np.float64)
+            for i in range(2):
+                sess.act(obs64)
+                sess.observe(obs64 + 0.01, None)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                sess.act(obs64)
+                sess.observe(obs64 + 0.01 * (i + 1), None)
+            barrier()
+            sess_s = time.perf_counter() - t0
+            e2e["session"] = {"value": units * args.steps / sess_s, "unit": UNIT, "ms_per_step": 1e3 * sess_s / args.steps,
+                              "h2d_bytes_per_step": 4 * m * env.obs_dim * 2, "d2h_bytes_per_step": 4 * m * env.act_dim,
+                              "what": "PlannerSession.act + observe: warm start / init_var / history buffers resident on the device"}
+    if sampler is not None and sampler.proc is not None and len(sampler.rows) < 5:
+        # the timed region of a small workload is over before nvidia-smi has produced a sample: keep the same decisions running
+        # under the sampler for a moment so that the clocks line describes the GPU under THIS load
+        t_end = time.perf_counter() + 0.8
+        i = 0
+        while time.perf_counter() < t_end:
+            step(1000 + i)
+            i += 1
+        barrier()
+
+    In = env.proc_obs_dim + env.act_dim + (10 if cfg["context"] else 0)
+    fpu = flops_per_unit(In, 200, env.obs_dim, cfg["deterministic"])
+    n_rank = n_total if by_env else n_total // world
+    units_per_launch = m * n_rank * p * h            # one launch = one CEM iteration of this rank's rows
+    launch_ms = statistics.mean(kernel_ms) / 5.0
+    res = dict(value=units * args.steps / (total_ms * 1e-3), ms_per_step=total_ms / args.steps, launch_ms=launch_ms,
+               kernel=eng.kernel_name, launches=int(launches), fpu=fpu, units_per_launch=units_per_launch,
+               achieved=units_per_launch * fpu / (launch_ms * 1e-3) / 1e12,
+               kernel_share=statistics.mean(kernel_ms) / (total_ms / args.steps), wall=wall, e2e=e2e,
+               fused=bool(planner is not None and planner.fused), E=E, p=p, h=h, n=n_total, m=m)
+    eng.close()
+    return res
+
+
+def leg_summary(r, what):
+    return {"what": what, "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "rollout_launch_ms": r["launch_ms"],
+            "kernel": r["kernel"], "kernel_share_of_step": r["kernel_share"], "achieved_tflops_per_gpu": r["achieved"]}
+
+
+def run_engine(args, rank, world, local_rank):
+    import torch
+    from cadm_b200.synth import WORKLOAD_NAMES
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
+    sweep = bool(args.cand or args.part)
+    base_n = args.cand or {"C1": 200, "C2": 200, "C3": 200, "C4": 1000}[args.config]
+    strong = world == 1 or args.scaling == "strong" or sweep
+    n_primary = base_n if strong else base_n * world
+    if n_primary % world:
+        raise SystemExit(f"{n_primary} candidates do not split over {world} ranks")
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    prim = measure_leg(args, rank, world, local_rank, args.config, args.m, n_primary, args.part, "candidates", flush,
+                       timed_e2e=True, sampler=sampler)
     clocks = sampler.stop()
 
+    # ---- the other legs of a multi-GPU line (BASELINE.json: the NAMED configs at 1 / 2 / 4 / 8 GPUs are strong scaling)
+    legs = {}
+    if world > 1 and not sweep and not args.no_extra_legs:
+        other = "weak" if strong else "strong"
+        n_other = base_n * world if strong else base_n
+        r = measure_leg(args, rank, world, local_rank, args.config, args.m, n_other, 0, "candidates", flush)
+        legs[other] = leg_summary(r, f"{args.config}, n={n_other} candidates over {world} GPUs ({n_other // world} per GPU), m={args.m}")
+        if args.config == "C2" and 1000 % world == 0:
+            r = measure_leg(args, rank, world, local_rank, "C4", 1, 1000, 0, "candidates", flush)
+            legs["strong_C4"] = leg_summary(r, f"BASELINE configs[3]: Ant PE-TS + CaDM, n=1000 candidates over {world} GPUs ({1000 // world} per GPU), m=1")
+        r = measure_leg(args, rank, world, local_rank, args.config, 10, base_n, 0, "envs", flush)
+        legs["env_sharded"] = leg_summary(r, f"{args.config}, m=10 environments PER GPU ({10 * world} in all), n={base_n}: environments sharded, "
+                                             "no exchange during planning (cadm/samplers/sampler.py:107-120 plans 10-20 environments per call)")
     if rank != 0:
         return
     peaks = load_peaks()
-    In = env.proc_obs_dim + env.act_dim + (10 if cfg["context"] else 0)
-    fpu = flops_per_unit(In, 200, env.obs_dim, cfg["deterministic"])
-    # dominant kernel: the rollout kernel; one launch = one CEM iteration of this rank's candidates
-    units_per_launch = m * (n_total // world) * p * h
-    launch_ms = statistics.mean(kernel_ms) / 5.0
-    achieved = units_per_launch * fpu / (launch_ms * 1e-3) / 1e12
-    traffic, traffic_src = ncu_traffic(eng.kernel_name) if (world == 1 and args.config == "C2" and m == 1 and not (args.cand or args.part)) else (None, None)
+    E, p, h = prim["E"], prim["p"], prim["h"]
+    single_default = world == 1 and args.config == "C2" and args.m == 1 and not sweep
+    traffic, traffic_src = ncu_traffic(prim["kernel"]) if single_default else (None, None)
+    name = WORKLOAD_NAMES[args.config] if not sweep else f"HalfCheetah PE-TS CEM sweep cell (ens={E}, part={p}, cand={n_primary}, horizon={h})"
     line = {
-        "metric": METRIC, "value": units * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if args.cand else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (WORKLOAD_NAMES[args.config] if not (args.cand or args.part) else
-                                f"HalfCheetah PE-TS CEM sweep cell (ens={E}, part={p}, cand={n_total}, horizon={h})") + f", m={m}" + (f", n={n_total} sharded {world} x {n_total // world}" if world > 1 else ""),
-                   "precision": args.precision, "kernel": eng.kernel_name,
+        "metric": METRIC, "value": prim["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": prim["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name + f", m={args.m}" + (f", n={n_primary} sharded {world} x {n_primary // world}" if world > 1 else ""),
+                   "scaling": ("strong: the named config's candidates split over the GPUs" if strong else
+                               f"weak: {base_n} candidates per GPU (n = {n_primary})") if world > 1 else "single GPU",
+                   "precision": args.precision, "kernel": prim["kernel"],
                    "l2": "flushed between steps (256 MiB write outside the timed events); weights (2.7 MB) are L2-resident by design within a step",
                    "parallelism": (f"candidates sharded over {world} GPU(s), 1 all-gather of [m, n/G] returns per CEM iteration, "
-                                   + ("fused into the particle-mean kernel over peer memory (NVLink stores + device flags)" if planner.fused else "NCCL"))
+                                   + ("fused into the refit kernel over peer memory (NVLink stores + device flags)" if prim["fused"] else "NCCL"))
                    if world > 1 else "single GPU"},
-        "e2e": e2e,
-        "gpu_launches": int(launches),
+        "e2e": prim["e2e"],
+        "gpu_launches": prim["launches"],
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_burst"], "traffic": traffic, "traffic_source": traffic_src, "kernel": eng.kernel_name,
-                     "launch_ms": launch_ms, "flop_per_unit": fpu, "units_per_launch": units_per_launch,
+        "roofline": {"bound": "tensor", "achieved": prim["achieved"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                     "frac": prim["achieved"] / peaks["bf16_burst"], "traffic": traffic, "traffic_source": traffic_src, "kernel": prim["kernel"],
+                     "launch_ms": prim["launch_ms"], "flop_per_unit": prim["fpu"], "units_per_launch": prim["units_per_launch"],
                      "peak_source": f"{peaks['src']} bf16 dense burst (MEASURED_PEAKS.json)",
-                     "kernel_share_of_step": statistics.mean(kernel_ms) / (total_ms / args.steps)},
-        "wall_s_timed_loop": wall,
+                     "kernel_share_of_step": prim["kernel_share"]},
+        "wall_s_timed_loop": prim["wall"],
     }
+    if legs:
+        line["legs"] = legs
     if world == 1 and not args.no_cpu_baseline:
+        from cadm_b200.synth import build_model
+        model, env, cfg = build_model(args.config, m_max=max(args.m, 1), candidates=n_primary, particles=args.part or None,
+                                      precision=args.precision, device=dev)
         line["cpu_baseline"] = cpu_baseline_leg(args, model, env, cfg)
     print(json.dumps(line), flush=True)
 
@@ -381,6 +425,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cand", type=int, default=0, help="override the candidate count (C5 sweep cells)")
     ap.add_argument("--part", type=int, default=0, help="override the particle count (C5 sweep cells)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: which leg is the line's `value` -- weak = the config's candidate count PER GPU, strong = the named "
+                         "config split over the GPUs; the other leg, C4 strong and the environment-sharded leg go under `legs`")
+    ap.add_argument("--no-extra-legs", action="store_true", help="N > 1: only the primary leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cadm_b200" else args.warmup
 

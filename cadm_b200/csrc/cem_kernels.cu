@@ -30,7 +30,7 @@ __global__ void sample_actions_kernel(const SampleParams S) {
         const bool need_rng = (S.mode == 2) ? (S.u_int == nullptr) : (S.z == nullptr);
         if (need_rng) {
             const uint32_t stream = S.mode == 0 ? kStreamZ : (S.mode == 1 ? kStreamU : kStreamUD);
-            w = philox(S.seed, (uint32_t)j, (uint32_t)ng, (uint32_t)mi, ((uint32_t)S.it << 8) | stream);
+            w = philox(S.seed, (uint32_t)j, (uint32_t)ng, (uint32_t)(mi + S.env_offset), ((uint32_t)S.it << 8) | stream);
         }
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
@@ -75,43 +75,6 @@ cudaError_t launch_particle_mean(const float* ret_p, float* out, int count, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// mean over particles FUSED with the all-gather of the candidate returns (multi-GPU): the slice is written into every
-// rank's returns buffer through peer pointers (NVLink / NVSwitch stores), then flag `rank` of every rank is set to the
-// iteration's epoch with system-scope release ordering.  The refit kernel of each rank spins on its own flags.
-// ------------------------------------------------------------------------------------------------
-__global__ void particle_mean_scatter_kernel(const float* __restrict__ ret_p, int count, int p, unsigned char* const* peers,
-                                             int world, long long slice_off, long long flag_off, int epoch, int* block_counter) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) {
-        const float* r = ret_p + (size_t)i * p;
-        float s = 0.f;
-        for (int k = 0; k < p; ++k) s += r[k];           // the same fixed order as particle_mean_kernel: results do not depend on G
-        const float v = s / (float)p;
-        for (int g = 0; g < world; ++g) reinterpret_cast<float*>(peers[g] + slice_off)[i] = v;
-    }
-    __threadfence_system();                               // this block's stores are visible system-wide ...
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int done = atomicAdd(block_counter, 1);     // ... before it is counted
-        if (done == (int)gridDim.x - 1) {                 // last block: the whole slice has landed everywhere
-            *block_counter = 0;
-            __threadfence_system();
-            for (int g = 0; g < world; ++g) {
-                int* flag = reinterpret_cast<int*>(peers[g] + flag_off);
-                asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-            }
-        }
-    }
-}
-
-cudaError_t launch_particle_mean_scatter(const float* ret_p, int count, int p, unsigned char* const* peers, int world,
-                                         long long slice_off, long long flag_off, int epoch, int* block_counter, cudaStream_t stream) {
-    particle_mean_scatter_kernel<<<(count + 255) / 256, 256, 0, stream>>>(ret_p, count, p, peers, world, slice_off, flag_off, epoch,
-                                                                          block_counter);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
 // elite selection + refit (core/utils.py:171-182); one CTA per environment
 // ------------------------------------------------------------------------------------------------
 
@@ -131,7 +94,7 @@ __device__ __forceinline__ float elite_action(const RefitParams& R, int mi, int 
     float z;
     if (R.z) z = R.z[((size_t)mi * R.n_global + ni) * hA + k];
     else {
-        uint4 w = philox(R.seed, (uint32_t)(k >> 2), (uint32_t)ni, (uint32_t)mi, ((uint32_t)R.it << 8) | kStreamZ);
+        uint4 w = philox(R.seed, (uint32_t)(k >> 2), (uint32_t)ni, (uint32_t)(mi + R.env_offset), ((uint32_t)R.it << 8) | kStreamZ);
         z = trunc_normal(word_of(w, k & 3));
     }
     return cem_action_value(mu0, var0, z);
@@ -287,7 +250,7 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
             const int ni = s_el[jx];
             const bool local = ni >= R.n_offset && ni < R.n_offset + R.n_local;
             uint4 w = make_uint4(0, 0, 0, 0);
-            if (!local && !R.z) w = philox(R.seed, (uint32_t)b, (uint32_t)ni, (uint32_t)mi, ((uint32_t)R.it << 8) | kStreamZ);
+            if (!local && !R.z) w = philox(R.seed, (uint32_t)b, (uint32_t)ni, (uint32_t)(mi + R.env_offset), ((uint32_t)R.it << 8) | kStreamZ);
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
                 const int k = 4 * b + l;

@@ -26,6 +26,7 @@ struct RolloutParams {
     int E, p, q;              // q = p / E
     int n_local, n_global, n_offset;
     int m, h;
+    int env_offset;           // index of environment 0 in an environment-sharded decision (enters the Philox counters only)
     int deterministic, discrete;
     int it;                   // CEM iteration (context pairing + RNG counter)
     int ctx_mode;             // 0 none, 1 reference pairing, 2 matched pairing, 3 per-row (predict)

@@ -33,6 +33,7 @@ struct Engine {
     int tcs_rows = 0;                  // rows per tile of the swapped kernel (0 = pick)
     bool trace = false;                // clock64 phase trace of CTA 0 (perturbs that CTA: off unless asked for)
     int tcs_skew = 0;                  // start-delay step (cycles) that de-phases the CTAs of the swapped kernel
+    int env_offset = 0;                // first environment of this engine in an environment-sharded decision (Philox counters)
     int tcs_kps = 4;                   // K16 blocks per weight stage the swapped image is packed with
     float* bpack_tc = nullptr;
     int Np16 = 0, NHp16 = 0, nkb0 = 0, nkbH = 0;
@@ -59,10 +60,10 @@ struct Engine {
     float* ret_p = nullptr;
     float* returns_buf = nullptr;
     float* returns_log = nullptr;
-    // exchange block (one allocation, exported over CUDA IPC): [2 parities][world, m_max, n_local] returns | [2][world] flags
+    // exchange block (one allocation, exported over CUDA IPC): [2 parities][world, m_max, n_local] returns | [2][world, m_max] flags
     unsigned char* xchg = nullptr;
-    size_t xchg_ret_bytes = 0, xchg_bytes = 0;
-    int* block_counter = nullptr;
+    size_t xchg_ret_bytes = 0, xchg_flag_bytes = 0, xchg_bytes = 0;
+    long long peer_timeout_cycles = 60000000000ll;   // bound of the device-side wait for a peer's slice (~30 s at 2 GHz); cadm_set_option "peer_timeout_ms"
     unsigned char** peer_tab = nullptr;      // device array [world]: every rank's exchange block as seen from this device
     std::vector<void*> peer_open;            // mappings to close
     bool peers_on = false;
@@ -124,6 +125,7 @@ RolloutParams base_params(Engine* E) {
     P.E = c.ensemble; P.p = c.particles; P.q = E->q;
     P.n_local = E->n_local; P.n_global = c.candidates; P.n_offset = E->n_offset;
     P.h = c.horizon;
+    P.env_offset = E->env_offset;
     P.deterministic = c.deterministic; P.discrete = c.discrete;
     P.max_torque = c.max_torque > 0.f ? c.max_torque : 2.0f;
     P.Kp0 = E->Kp0; P.Hp = E->Hp; P.NHp = E->NHp;
@@ -307,10 +309,10 @@ int cadm_plan_create(const CadmConfig* cfg, void** handle) {
     A(dalloc(E, &E->actions_int, mm * E->n_local * c.horizon));
     A(dalloc(E, &E->ret_p, mm * E->n_local * c.particles));
     E->xchg_ret_bytes = (mm * c.candidates * sizeof(float) + 255) / 256 * 256;
-    E->xchg_bytes = 2 * E->xchg_ret_bytes + 2 * 256 * ((c.world * sizeof(int) + 255) / 256);
+    E->xchg_flag_bytes = ((size_t)c.world * mm * sizeof(int) + 255) / 256 * 256;
+    E->xchg_bytes = 2 * E->xchg_ret_bytes + 2 * E->xchg_flag_bytes;
     A(dalloc(E, &E->xchg, E->xchg_bytes));
     E->returns_buf = reinterpret_cast<float*>(E->xchg);          // parity 0 doubles as the buffer of the NCCL path
-    A(dalloc(E, &E->block_counter, 1));
     A(dalloc(E, &E->peer_tab, (size_t)c.world));
     A(dalloc(E, &E->returns_log, (size_t)c.cem_iters * mm * c.candidates));
     A(dalloc(E, &E->elites_log, (size_t)c.cem_iters * mm * c.num_elites));
@@ -546,7 +548,7 @@ int cadm_cem_rollout(void* handle, int32_t it, uint64_t seed, const float* z, co
     E->cur_z = z;
     SampleParams S{};
     S.m = m; S.n_local = E->n_local; S.n_global = c.candidates; S.n_offset = E->n_offset; S.hA = E->hA; S.A = c.act_dim;
-    S.it = it; S.mode = 0; S.seed = seed;
+    S.it = it; S.mode = 0; S.seed = seed; S.env_offset = E->env_offset;
     S.mean = E->mean; S.var = E->var;
     S.z = z ? z + (size_t)it * m * c.candidates * E->hA : nullptr;
     S.actions = E->actions;
@@ -565,19 +567,14 @@ int cadm_cem_rollout(void* handle, int32_t it, uint64_t seed, const float* z, co
 
     if (c.world > 1) {      // single rank: the refit kernel folds the particle mean in
         if (E->peers_on) {
-            // fused: particle mean + all-gather over peer memory; parity = epoch & 1 so that a rank one iteration ahead
-            // cannot overwrite a slice a slower rank is still reading
+            // fused: the refit kernel averages the particles, stores the slice into every rank's exchange block and waits for the
+            // others (cem_kernels.cu); parity = epoch & 1 so that a rank one iteration ahead cannot overwrite a slice a slower
+            // rank is still reading
             ++E->epoch;
-            const long long par = E->epoch & 1;
-            const long long slice_off = par * (long long)E->xchg_ret_bytes + (long long)c.rank * m * E->n_local * sizeof(float);
-            const long long flag_off = 2 * (long long)E->xchg_ret_bytes + par * 256 * (long long)((c.world * sizeof(int) + 255) / 256) +
-                                       (long long)c.rank * sizeof(int);
-            CU(E, launch_particle_mean_scatter(E->ret_p, m * E->n_local, c.particles, E->peer_tab, c.world, slice_off, flag_off, E->epoch,
-                                               E->block_counter, s));
         } else {
             CU(E, launch_particle_mean(E->ret_p, E->returns_buf + (size_t)c.rank * m * E->n_local, m * E->n_local, c.particles, s));
+            E->launches++;
         }
-        E->launches++;
     }
     return CADM_OK;
 }
@@ -594,15 +591,19 @@ static int refit_common(Engine* E, int it, uint64_t seed, const float* z, cudaSt
     const int m = E->m;
     RefitParams R{};
     R.m = m; R.n_local = E->n_local; R.n_global = c.candidates; R.n_offset = E->n_offset; R.world = c.world;
-    R.h = c.horizon; R.A = c.act_dim; R.k_elites = c.num_elites; R.it = it;
+    R.h = c.horizon; R.A = c.act_dim; R.k_elites = c.num_elites; R.it = it; R.env_offset = E->env_offset;
     R.npad = next_pow2(c.candidates);
     R.alpha = c.alpha; R.seed = seed;
     R.returns_buf = E->returns_buf; R.actions = E->actions;
     if (c.world > 1 && E->peers_on) {
         const long long par = E->epoch & 1;
-        R.returns_buf = reinterpret_cast<const float*>(E->xchg + par * E->xchg_ret_bytes);
-        R.peer_flags = reinterpret_cast<const int*>(E->xchg + 2 * E->xchg_ret_bytes + par * 256 * ((c.world * sizeof(int) + 255) / 256));
+        R.peers = E->peer_tab;
+        R.slice_off = par * (long long)E->xchg_ret_bytes;
+        R.flag_off = 2 * (long long)E->xchg_ret_bytes + par * (long long)E->xchg_flag_bytes;
+        R.ret_p_local = E->ret_p;
+        R.rank = c.rank; R.m_max = c.m_max;
         R.peer_epoch = E->epoch;
+        R.timeout_cycles = E->peer_timeout_cycles;
         R.peer_timeout = E->peer_timeout_dev;
     }
     R.z = z ? z + (size_t)it * m * c.candidates * E->hA : nullptr;
@@ -628,9 +629,14 @@ int cadm_cem_finish(void* handle, float* mean, float* var, float* returns, int32
     Engine* E = H(handle);
     if (!E) return CADM_ERR_ARG;
     if (!E->in_flight) return fail(E, CADM_ERR_STATE, "cadm_cem_begin has not been called");
-    if (int r = check_peers(E)) { E->in_flight = false; return r; }
     const CadmConfig& c = E->cfg;
     cudaStream_t s = (cudaStream_t)stream;
+    if (E->peers_on) {
+        // the refit kernels report a peer that never delivered through a host-mapped word; they are asynchronous, so the word is
+        // only meaningful once they have run: wait for them here and fail THIS decision instead of the next one
+        CU(E, cudaStreamSynchronize(s));
+        if (int r = check_peers(E)) { E->in_flight = false; return r; }
+    }
     const size_t m = E->m;
     if (mean) CU(E, cudaMemcpyAsync(mean, E->mean, m * E->hA * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (var) CU(E, cudaMemcpyAsync(var, E->var, m * E->hA * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -649,7 +655,9 @@ int cadm_plan_cem(void* handle, int32_t m, const float* obs, const float* cp_obs
                   float* mean, float* var, float* returns, int32_t* elites, void* stream) {
     Engine* E = H(handle);
     if (!E) return CADM_ERR_ARG;
-    if (E->cfg.world != 1) return fail(E, CADM_ERR_STATE, "cadm_plan_cem is the single-rank form; use the phase calls when world > 1");
+    if (E->cfg.world != 1 && !E->peers_on)
+        return fail(E, CADM_ERR_STATE, "cadm_plan_cem at world > 1 needs the fused exchange (cadm_peer_attach); without it use the phase calls "
+                                       "with your own all-gather between cadm_cem_rollout and cadm_cem_refit");
     if (int r = cadm_cem_begin(handle, m, obs, cp_obs, cp_act, init_mean, init_var, stream)) return r;
     for (int it = 0; it < E->cfg.cem_iters; ++it) {
         if (int r = cadm_cem_rollout(handle, it, seed, z, eps, stream)) return r;
@@ -664,7 +672,8 @@ int cadm_plan_cem_host(void* handle, int32_t m, const float* obs_host, const flo
     Engine* E = H(handle);
     if (!E) return CADM_ERR_ARG;
     const CadmConfig& c = E->cfg;
-    if (c.world != 1) return fail(E, CADM_ERR_STATE, "cadm_plan_cem_host is the single-rank form");
+    if (c.world != 1 && !E->peers_on)
+        return fail(E, CADM_ERR_STATE, "cadm_plan_cem_host at world > 1 needs the fused exchange (cadm_peer_attach)");
     if (m < 1 || m > c.m_max) return fail(E, CADM_ERR_ARG, "m out of range (1..m_max)");
     if (!obs_host || !init_mean_host || !init_var_host || !action_host) return fail(E, CADM_ERR_ARG, "null host pointer");
     if (c.ctx_dim > 0 && (!cp_obs_host || !cp_act_host)) return fail(E, CADM_ERR_ARG, "cp_obs/cp_act are required for a context model");
@@ -712,7 +721,7 @@ int cadm_session_act(void* handle, int32_t m, const float* obs_host, uint64_t se
     Engine* E = H(handle);
     if (!E) return CADM_ERR_ARG;
     const CadmConfig& c = E->cfg;
-    if (c.world != 1) return fail(E, CADM_ERR_STATE, "sessions are single-rank");
+    if (c.world != 1 && !E->peers_on) return fail(E, CADM_ERR_STATE, "sessions at world > 1 need the fused exchange (cadm_peer_attach)");
     if (c.discrete) return fail(E, CADM_ERR_UNSUPPORTED, "sessions plan with CEM (continuous actions)");
     if (m < 1 || m > c.m_max || !obs_host || !action_host) return fail(E, CADM_ERR_ARG, "bad arguments");
     if (!E->s_var_set) return fail(E, CADM_ERR_STATE, "cadm_session_reset has not been called");
@@ -777,7 +786,7 @@ int cadm_plan_rs(void* handle, int32_t m, const float* obs, const float* cp_obs,
     if (c.ctx_dim > 0)
         if (int r = run_encoder(E, m, cp_obs, cp_act, E->ctx, s)) return r;
     SampleParams S{};
-    S.m = m; S.n_local = E->n_local; S.n_global = c.candidates; S.n_offset = 0; S.A = c.act_dim; S.it = 0; S.seed = seed;
+    S.m = m; S.n_local = E->n_local; S.n_global = c.candidates; S.n_offset = 0; S.A = c.act_dim; S.it = 0; S.seed = seed; S.env_offset = E->env_offset;
     if (c.discrete) { S.mode = 2; S.hA = c.horizon; S.u_int = u_int; S.actions_int = E->actions_int; }
     else { S.mode = 1; S.hA = E->hA; S.z = u; S.actions = E->actions; }
     CU(E, launch_sample_actions(S, s));
@@ -865,7 +874,7 @@ int cadm_peer_attach(void* handle, const void* ipc_handles, int32_t count) {
         CU(E, cudaHostGetDevicePointer(reinterpret_cast<void**>(&E->peer_timeout_dev), E->peer_timeout_host, 0));
     }
     CU(E, cudaMemcpy(E->peer_tab, tab.data(), sizeof(unsigned char*) * c.world, cudaMemcpyHostToDevice));
-    CU(E, cudaMemset(E->xchg + 2 * E->xchg_ret_bytes, 0, E->xchg_bytes - 2 * E->xchg_ret_bytes));      // flags: epoch 0
+    CU(E, cudaMemset(E->xchg + 2 * E->xchg_ret_bytes, 0, 2 * E->xchg_flag_bytes));      // flags: epoch 0
     CU(E, cudaDeviceSynchronize());
     E->epoch = 0;
     E->peers_on = true;
@@ -888,6 +897,17 @@ int cadm_set_option(void* handle, const char* name, int32_t value) {
         if (value < 1 || value > 4) return fail(E, CADM_ERR_ARG, "tcs_kps must be in 1..4");
         if (E->have_weights) return fail(E, CADM_ERR_STATE, "tcs_kps must be set before cadm_plan_set_weights");
         E->tcs_kps = value;
+    } else if (k == "env_offset") {
+        if (value < 0) return fail(E, CADM_ERR_ARG, "env_offset must be non-negative");
+        if (E->in_flight) return fail(E, CADM_ERR_STATE, "env_offset cannot change in the middle of a decision");
+        E->env_offset = value;
+    } else if (k == "peer_timeout_ms") {
+        if (value < 1) return fail(E, CADM_ERR_ARG, "peer_timeout_ms must be positive");
+        E->peer_timeout_cycles = (long long)value * 2000000ll;           // clock64 ticks at ~2 GHz
+    } else if (k == "peer_clear_timeout") {
+        // after a peer was slow rather than dead: forget the report so that the engine can be used again (the caller has
+        // re-synchronised the ranks, e.g. with a process-group barrier)
+        if (E->peer_timeout_host) *reinterpret_cast<volatile int*>(E->peer_timeout_host) = 0;
     } else if (k == "trace") {
         E->trace = value != 0;
     } else if (k == "tcs_skew") {

@@ -6,6 +6,7 @@ namespace cadm {
 
 struct SampleParams {
     int m, n_local, n_global, n_offset, hA, A;
+    int env_offset;           // added to the environment index in the Philox counters
     int it;
     int mode;                 // 0: CEM truncated normal, 1: uniform(-1,1), 2: discrete uniform ints (hA = h)
     unsigned long long seed;
@@ -20,6 +21,7 @@ struct SampleParams {
 struct RefitParams {
     int m, n_local, n_global, n_offset, world;
     int h, A, k_elites, it;
+    int env_offset;                 // added to the environment index in the Philox counters
     int npad;                       // power of two >= n_global
     float alpha;
     unsigned long long seed;

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
                         planner_row(P, e, rl, mi, nl, pi);
                         src = mi * P.n_local + nl;
                         const int ng = P.n_offset + nl;
-                        rid = (mi * P.n_global + ng) * P.p + pi;
+                        rid = ((mi + P.env_offset) * P.n_global + ng) * P.p + pi;
                         cidx = P.ctx_mode ? planner_ctx_index(P, e, mi, pi) : 0;
                         const int jq = pi - e * P.q;
                         er = e * (P.q * P.m * P.n_global) + (jq * P.m + mi) * P.n_global + ng;

@@ -141,6 +141,9 @@ class PlannerModelBase:
         self._push_params()
 
     def _push_params(self):
+        # every repack counts as "the parameters may have changed": a trainer kept from an earlier fit() is rebuilt from the
+        # arrays unless fit() itself did the repack (training.trainer_done)
+        self._params_version = getattr(self, "_params_version", 0) + 1
         d = self._dyn
         self.engine.set_weights(d["W"] + [d["W_mu"], d["W_lv"]], d["b"] + [d["b_mu"], d["b_lv"]],
                                 d["max_logvar"], d["min_logvar"])
@@ -184,10 +187,33 @@ class PlannerModelBase:
             shp = (obs.shape[0], self.n_forwards, self.action_space_dims)
             if tuple(np.shape(cem_init_mean)) != shp or tuple(np.shape(cem_init_var)) != shp:
                 raise ValueError(f"cem_init_mean / cem_init_var must be {shp}")
+            if getattr(getattr(self.engine, "cfg", None), "world", 1) > 1:
+                return self._plan_sharded(obs, cp_obs, cp_act, cem_init_mean, cem_init_var)
             return self.engine.plan_cem_host(obs, cem_init_mean, cem_init_var, cp_obs, cp_act, seed=self._next_seed())
         if self.use_cem:
             raise ValueError("model was built with use_cem=True: cem_init_mean / cem_init_var must be fed")
         return self._rs(obs, cp_obs, cp_act)
+
+    # ------------------------------------------------------------------ planning over the GPUs of one box
+    def sharded_planner(self, group=None, fused=None):
+        """The candidate-sharded planner of this model's engine (world > 1; created on first use, then kept).  Every rank
+        builds the model with its own `rank` / the common `world` and the same `seed`, and calls get_action() with the
+        same inputs: the decision is SPMD and every rank returns the same plan (cadm_b200/parallel.py)."""
+        if getattr(self, "_sharded", None) is None:
+            from ..parallel import ShardedCEMPlanner
+            self._sharded = ShardedCEMPlanner(self.engine, group=group, fused=fused)
+        return self._sharded
+
+    def _plan_sharded(self, obs, cp_obs, cp_act, cem_init_mean, cem_init_var):
+        planner = self.sharded_planner()
+        seed = self._next_seed()
+        if planner.fused:
+            # the exchange happens inside the library (peer memory): the single host call works at world > 1 as it is
+            return self.engine.plan_cem_host(obs, cem_init_mean, cem_init_var, cp_obs, cp_act, seed=seed)
+        out = planner.plan(obs, cem_init_mean, cem_init_var, cp_obs, cp_act, seed=seed, logs=False)
+        mean = out["mean"]
+        mean = mean.detach().cpu().numpy() if hasattr(mean, "detach") else np.asarray(mean)
+        return np.minimum(np.maximum(mean.astype(np.float32), -1.0), 1.0)      # get_action's clip (reference :205-206)
 
     def _rs(self, obs, cp_obs, cp_act):
         out = self.engine.plan_rs(obs, cp_obs, cp_act, seed=self._next_seed())

@@ -22,6 +22,53 @@ def preproc_torch(env_name, obs):
     return obs
 
 
+class TFAdam:
+    """tf.train.AdamOptimizer of TensorFlow 1.x (the reference's optimiser, mlp_ensemble_cem_dynamics.py:169,
+    mlp_cadm_ensemble_cem_dynamics.py:316), "epsilon hat" form:
+        m <- b1 m + (1 - b1) g ;  v <- b2 v + (1 - b2) g^2 ;  theta <- theta - lr sqrt(1 - b2^t) / (1 - b1^t) * m / (sqrt(v) + eps)
+    (torch.optim.Adam puts eps inside the bias correction).  The slots m, v and the step count t belong to the MODEL: the
+    reference creates the optimiser once, in the constructor, so they persist across fit() calls on the growing dataset."""
+
+    def __init__(self, params, lr, b1=0.9, b2=0.999, eps=1e-8):
+        self.params = list(params)
+        self.lr, self.b1, self.b2, self.eps, self.t = float(lr), b1, b2, eps, 0
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            p.grad = None
+
+    @torch.no_grad()
+    def step(self):
+        self.t += 1
+        lr_t = self.lr * (1.0 - self.b2 ** self.t) ** 0.5 / (1.0 - self.b1 ** self.t)
+        for p, m, v in zip(self.params, self.m, self.v):
+            if p.grad is None:
+                continue
+            g = p.grad
+            m.mul_(self.b1).add_(g, alpha=1.0 - self.b1)
+            v.mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
+            p.addcdiv_(m, v.sqrt().add_(self.eps), value=-lr_t)
+
+
+def model_trainer(model, make):
+    """The model's trainer, created on the first fit() and REUSED afterwards (optimiser slots and step count persist, as in
+    the reference); rebuilt only when the parameters were replaced from outside (load / set_params / direct edits followed by
+    _push_params), which the model counts in `_params_version`."""
+    ver = getattr(model, "_params_version", 0)
+    tr = getattr(model, "_trainer", None)
+    if tr is None or getattr(model, "_trainer_version", None) != ver:
+        tr = make()
+        model._trainer = tr
+    return tr
+
+
+def trainer_done(model):
+    """After export + repack: the trainer's tensors and the model's arrays agree again."""
+    model._trainer_version = getattr(model, "_params_version", 0)
+
+
 class EnsembleNLLTrainer:
     """Parameters of the dynamics ensemble as torch leaves + the reference's loss and optimiser."""
 
@@ -41,7 +88,7 @@ class EnsembleNLLTrainer:
         # (core/utils.py:46-69)
         self.layer_decays = [float(wd[min(i, len(wd) - 1)]) for i in range(len(self.W))] + [float(wd[-1]), float(wd[-1])]
         if make_optimizer:
-            self.optimizer = torch.optim.Adam(self.parameters(), lr=learning_rate, betas=(0.9, 0.999), eps=1e-8)   # tf AdamOptimizer defaults
+            self.optimizer = TFAdam(self.parameters(), lr=learning_rate)          # tf.train.AdamOptimizer defaults
 
     def parameters(self):
         return self.W + self.b + [self.W_mu, self.b_mu, self.W_lv, self.b_lv, self.max_logvar, self.min_logvar]
@@ -163,8 +210,8 @@ def fit_ensemble(model, obs, act, obs_next, epochs=1000, valid_split_ratio=None,
 
     if device is None:
         device = model.engine.device if getattr(model, "engine", None) is not None else "cpu"
-    trainer = EnsembleNLLTrainer(model._dyn, model.env_name, model.deterministic, model.weight_decays, model.weight_decay_coeff,
-                                 model.learning_rate, device=device)
+    trainer = model_trainer(model, lambda: EnsembleNLLTrainer(model._dyn, model.env_name, model.deterministic, model.weight_decays,
+                                                              model.weight_decay_coeff, model.learning_rate, device=device))
     rolling, rolling_prev = None, None
     epoch = -1
     for epoch in range(epochs):
@@ -193,6 +240,7 @@ def fit_ensemble(model, obs, act, obs_next, epochs=1000, valid_split_ratio=None,
                 % (epoch, np.mean(mse_losses), np.mean(recon_losses)))
     trainer.export(model._dyn)
     model._push_params()                                            # repack for the engine (cadm_plan_set_weights)
+    trainer_done(model)
     return dict(epochs=epoch + 1, train_mse=float(np.mean(mse_losses)) if epoch >= 0 else None,
                 train_recon=float(np.mean(recon_losses)) if epoch >= 0 else None)
 
@@ -221,7 +269,7 @@ class CaDMTrainer:
         cwd = list(context_weight_decays)
         n = len(self.enc_W)                                          # hidden layers take [idx], the output layer [-1]
         self.enc_decays = [float(cwd[i]) for i in range(n - 1)] + [float(cwd[-1])]
-        self.optimizer = torch.optim.Adam(self.parameters(), lr=learning_rate, betas=(0.9, 0.999), eps=1e-8)
+        self.optimizer = TFAdam(self.parameters(), lr=learning_rate)
 
     def parameters(self):
         return self.enc_W + self.enc_b + self.fwd.parameters() + (self.back.parameters() if self.back is not None else [])
@@ -364,9 +412,9 @@ def fit_cadm_ensemble(model, obs, act, obs_next, cp_obs, cp_act, future_bool, ep
 
     if device is None:
         device = model.engine.device if getattr(model, "engine", None) is not None else "cpu"
-    trainer = CaDMTrainer(model._enc, model._dyn, model._back, model.env_name, model.deterministic, model.weight_decays,
-                          model.context_weight_decays, model.weight_decay_coeff, model.back_coeff, model.learning_rate,
-                          device=device)
+    trainer = model_trainer(model, lambda: CaDMTrainer(model._enc, model._dyn, model._back, model.env_name, model.deterministic,
+                                                       model.weight_decays, model.context_weight_decays, model.weight_decay_coeff,
+                                                       model.back_coeff, model.learning_rate, device=device))
     rolling, rolling_prev = None, None
     epoch = -1
     mse_losses, back_mse_losses, recon_losses = [], [], []
@@ -399,6 +447,7 @@ def fit_cadm_ensemble(model, obs, act, obs_next, cp_obs, cp_act, future_bool, ep
         rolling_prev = rolling                                      # :560 (the PE-TS loop has no such line)
     trainer.export(model._enc, model._dyn, model._back)
     model._push_params()                                            # repack for the engine (weights + encoder)
+    trainer_done(model)
     mean = lambda l: float(np.mean(l)) if l else None
     return dict(epochs=epoch + 1, train_mse=mean(mse_losses), train_back_mse=mean(back_mse_losses),
                 train_recon=mean(recon_losses))

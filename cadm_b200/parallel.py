@@ -129,9 +129,11 @@ class EnvShardedPlanner:
         context tensor as [m, E, C] and so mixes environments when m > 1 and E > 1; a block of m/G environments
         cannot reproduce that, therefore a backend with a context encoder must use context_layout="matched" (or
         E == 1) unless `allow_local_context=True` accepts the pairing of the local block;
-      * seed-only noise is keyed by the LOCAL environment index inside the kernels, so each rank plans with the key
-        seed + rank * 0x9E3779B97F4A7C15 (mod 2^64): independent streams per block, same distribution as the
-        unsharded decision, not the same numbers.
+      * seed-only noise is keyed by the GLOBAL environment index: the block's first environment is handed to the
+        engine as its "env_offset" option (added to the local index in every Philox counter, oracle/philox.py
+        `m_offset`), every rank uses the same key, and the block draws exactly the numbers it draws inside the
+        unsharded decision.  A backend without `set_option` (the test doubles) falls back to per-rank keys
+        seed + rank * 0x9E3779B97F4A7C15 (mod 2^64): same distribution, different numbers.
     `backend` is a PlannerEngine built with world=1 (or any object with `plan_cem` and `cfg`)."""
 
     def __init__(self, backend, rank=None, world=None, group=None, gather=True, allow_local_context=False):
@@ -186,8 +188,13 @@ class EnvShardedPlanner:
         out = dict(bounds=lo_all, mean=None, var=None)
         if hi > lo:
             zz = None if z is None else z[:, lo:hi]
+            if hasattr(self.backend, "set_option"):
+                self.backend.set_option("env_offset", lo)          # Philox counters see the global environment index
+                block_seed = int(seed)
+            else:
+                block_seed = self.rank_seed(seed)
             local = self.backend.plan_cem(obs[lo:hi], init_mean[lo:hi], init_var[lo:hi], self._rows(cp_obs, lo, hi),
-                                          self._rows(cp_act, lo, hi), seed=self.rank_seed(seed), z=zz,
+                                          self._rows(cp_act, lo, hi), seed=block_seed, z=zz,
                                           eps=self._slice_eps(eps, m, lo, hi), logs=logs)
             out.update(local)
         if not self.gather or self.world == 1:
@@ -196,18 +203,21 @@ class EnvShardedPlanner:
         c = self.backend.cfg
         hA = c.horizon * c.act_dim
         width = max(lo_all[r + 1] - lo_all[r] for r in range(self.world))
-        ref = out["mean"] if out["mean"] is not None else init_mean
-        as_t = (lambda a: a) if torch.is_tensor(ref) else (lambda a: torch.from_numpy(np.ascontiguousarray(a)))
-        like = as_t(ref)
-        mine = torch.zeros((2, width, hA), dtype=like.dtype, device=like.device)
+        # ONE dtype and ONE device on every rank, whether or not its block is empty: the engine's float32 on its CUDA device
+        # (a test double on the CPU may declare another `plan_dtype`); never taken from the caller's arrays
+        dev = getattr(self.backend, "device", None)
+        dev = torch.device(dev) if dev is not None else torch.device("cpu")
+        dt = getattr(self.backend, "plan_dtype", torch.float32)
+        as_t = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))).to(device=dev, dtype=dt)
+        mine = torch.zeros((2, width, hA), dtype=dt, device=dev)
         if hi > lo:
             mine[0, :hi - lo] = as_t(out["mean"]).reshape(hi - lo, hA)
             mine[1, :hi - lo] = as_t(out["var"]).reshape(hi - lo, hA)
-        full = torch.empty((self.world, 2, width, hA), dtype=like.dtype, device=like.device)
+        full = torch.empty((self.world, 2, width, hA), dtype=dt, device=dev)
         dist.all_gather_into_tensor(full.view(-1), mine.view(-1), group=self.group)
         self.collectives += 1
         parts = [full[r, :, :lo_all[r + 1] - lo_all[r]] for r in range(self.world)]
         both = torch.cat(parts, dim=1).reshape(2, m, c.horizon, c.act_dim)
-        conv = (lambda t: t) if torch.is_tensor(ref) else (lambda t: t.numpy())
+        conv = (lambda t: t) if torch.is_tensor(init_mean) or dev.type != "cpu" else (lambda t: t.numpy())
         out["mean"], out["var"] = conv(both[0]), conv(both[1])
         return out

@@ -53,7 +53,17 @@ class PlannerSession:
         self._next = pin(self.m * self.obs_dim, torch.float32)
         self._act = pin(self.m * self.act_dim, torch.float32)
         self._mask = pin(self.m, torch.uint8)
+        if cfg.world > 1 and not dynamics_model.sharded_planner().fused:
+            raise CadmError("PlannerSession at world > 1 needs the fused peer-memory exchange (GPUs of one node, CUDA IPC)")
+        # the session state (warm start, histories, counters) lives in the ENGINE, once: a new session takes it over and the
+        # previous one must not touch it any more
+        eng._session_token = self._token = object()
         self.reset()
+
+    def _own(self):
+        if getattr(self.engine, "_session_token", None) is not self._token:
+            raise CadmError("this PlannerSession is stale: another session was created on the same dynamics model and owns the "
+                            "engine's session state now (one live session per model)")
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.engine.device).cuda_stream)
@@ -61,7 +71,10 @@ class PlannerSession:
     def reset(self, idx=None):
         """Clear the warm start, the history and the counters of every environment (idx=None) or of the given ones."""
         e = self.engine
+        self._own()
         mask = None
+        with torch.cuda.device(e.device):
+            torch.cuda.current_stream(e.device).synchronize()          # observe() may still be reading the pinned mask
         if idx is not None:
             self._mask.zero_()
             self._mask.numpy()[np.atleast_1d(idx)] = 1
@@ -74,6 +87,7 @@ class PlannerSession:
         """One decision for every environment from the stored warm start / history; returns the clipped first actions [m, A]
         and shifts the warm start (sampler.py:107-120)."""
         e = self.engine
+        self._own()
         obs = np.asarray(obses, dtype=np.float32)
         if obs.shape != (self.m, self.obs_dim):
             raise ValueError(f"obses must be [{self.m}, {self.obs_dim}], got {obs.shape}")
@@ -90,6 +104,7 @@ class PlannerSession:
         float32 copies.  A host that holds float64 observations and wants the reference's rounding of the difference
         (subtract in float64, then round) passes it as `entry` [m, D]; it is stored as is."""
         e = self.engine
+        self._own()
         nxt = np.asarray(next_obses if entry is None else entry, dtype=np.float32)
         if nxt.shape != (self.m, self.obs_dim):
             raise ValueError(f"next_obses / entry must be [{self.m}, {self.obs_dim}], got {nxt.shape}")

@@ -152,11 +152,16 @@ int64_t cadm_cem_returns_slice_elems(void* handle);   /* m * n_local of the deci
 /* ---- fused all-gather over peer memory (optional; replaces the host-side ncclAllGather above) ----
  * Every rank exports its exchange block (returns buffer + arrival flags, one CUDA allocation) as a CUDA IPC handle,
  * the host exchanges the `world` handles (any transport; cadm_b200/parallel.py uses torch.distributed), and each rank
- * attaches them.  From then on cadm_cem_rollout averages over the particles AND stores the rank's slice into every
- * rank's returns buffer over NVLink in the same kernel, and cadm_cem_refit waits on the arrival flags on the device:
- * no collective call and no host synchronisation between the phases.  All ranks must be on one node and must call the
- * phases in lockstep (they do: the plan is data-independent).  The caller makes sure every rank has attached before
- * any rank starts a decision (a barrier after cadm_peer_attach). */
+ * attaches them.  From then on cadm_cem_refit does the exchange itself: the CTA of environment mi averages this rank's
+ * particle returns (core/utils.py:170), stores the slice into every rank's returns buffer over NVLink, publishes the
+ * iteration's epoch in flag (rank, mi) of every rank and waits on its own flags before the top-k -- no scatter kernel,
+ * no collective call and no host synchronisation between the phases.  With the peers attached the single-call forms
+ * (cadm_plan_cem, cadm_plan_cem_host, cadm_session_act) work at world > 1 as well: every rank calls them with the same
+ * inputs and arrives at the same plan.  All ranks must be on one node and must call in lockstep (they do: the plan is
+ * data-independent).  The caller makes sure every rank has attached before any rank starts a decision (a barrier after
+ * cadm_peer_attach).  The device-side wait is bounded (option "peer_timeout_ms", default 30 s): if a peer never delivers,
+ * cadm_cem_finish of that decision fails with CADM_ERR_CUDA; option "peer_clear_timeout" forgets the report once the
+ * caller has re-synchronised the ranks. */
 #define CADM_IPC_HANDLE_BYTES 64
 int cadm_peer_export(void* handle, void* ipc_handle_out /* CADM_IPC_HANDLE_BYTES */);
 int cadm_peer_attach(void* handle, const void* ipc_handles /* world x CADM_IPC_HANDLE_BYTES, rank order */, int32_t count);
@@ -169,8 +174,8 @@ int cadm_cem_refit(void* handle, int32_t it, void* stream);
  * returns [iters, m, n], elites [iters, m, k] int32 (global candidate ids).  Any pointer may be NULL. */
 int cadm_cem_finish(void* handle, float* mean, float* var, float* returns, int32_t* elites, void* stream);
 
-/* The whole decision for world == 1: begin + iters x (rollout, refit) + finish.  This is `_get_cem_action`
- * (mlp_ensemble_cem_dynamics.py:173-178 / mlp_cadm_...:320-328). */
+/* The whole decision: begin + iters x (rollout, refit) + finish (world == 1, or world > 1 with the peers attached).
+ * This is `_get_cem_action` (mlp_ensemble_cem_dynamics.py:173-178 / mlp_cadm_...:320-328). */
 int cadm_plan_cem(void* handle, int32_t m, const float* obs, const float* cp_obs, const float* cp_act,
                   const float* init_mean, const float* init_var, uint64_t seed, const float* z, const float* eps,
                   float* mean, float* var, float* returns, int32_t* elites, void* stream);
@@ -187,7 +192,8 @@ int cadm_plan_cem_host(void* handle, int32_t m, const float* obs_host, const flo
  * plan `prev_sol` (sampler.py:52,118-119), the constant `init_var` = 0.25 (:53), the K-step history buffers that feed the
  * context encoder and their fill counters (:94-97,164-178), and the per-episode resets (:55-57,190-195).  A control step
  * is then  cadm_session_act (H2D of obs [m, D], one decision, D2H of the clipped first actions [m, A])  followed, after
- * the environment step, by  cadm_session_observe (H2D of next_obs [m, D] and done [m]; asynchronous).  world == 1. */
+ * the environment step, by  cadm_session_observe (H2D of next_obs [m, D] and done [m]; asynchronous).  world == 1, or
+ * world > 1 with the peers attached (every rank keeps the same state and calls in lockstep). */
 int cadm_session_reset(void* handle, int32_t m, const uint8_t* mask_host /* [m] or NULL = all */, void* stream);
 int cadm_session_act(void* handle, int32_t m, const float* obs_host, uint64_t seed, float* action_host, void* stream);
 /* history entry: state_diff == 0: obs (sampler.py:166-177); 1: next_obs - obs, subtracted in fp32 (run_cadm_pets.py:137
@@ -225,7 +231,13 @@ int cadm_selftest_tcs_gemm(const float* X, const float* W, int32_t rows, int32_t
  *   "tcs_rows"    rows per tile of the swapped kernel: 0 = pick, else 16 / 32 / 48 / 64
  *   "tcs_kps"     K16 blocks per weight stage of the swapped kernel's image, 1..4 (before cadm_plan_set_weights)
  *   "tcs_skew"    start-delay step in cycles that de-phases the CTAs of the swapped kernel (0 = off)
- *   "trace"       1 = record the clock64 phase trace of CTA 0 (cadm_debug_trace); slows that CTA down */
+ *   "trace"       1 = record the clock64 phase trace of CTA 0 (cadm_debug_trace); selects the kernel instantiation that has
+ *                 the trace and the diagnostic switches compiled in (the production instantiation carries neither)
+ *   "env_offset"  index of this engine's first environment in a larger, environment-sharded decision: added to the local
+ *                 environment index in every Philox counter, so that a block of environments planned alone draws the same
+ *                 numbers as inside the whole decision (cadm_b200/parallel.py EnvShardedPlanner)
+ *   "peer_timeout_ms"     bound of the device-side wait for a peer's slice (fused all-gather), default 30000
+ *   "peer_clear_timeout"  forget a reported peer timeout (after the caller has re-synchronised the ranks) */
 int cadm_set_option(void* handle, const char* name, int32_t value);
 
 /* Diagnostic micro-benchmark: n_mma back-to-back tcgen05.mma (M=128, N, K=16, fp16) on resident shared-memory operands,

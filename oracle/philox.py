@@ -12,13 +12,13 @@ Counter layout (c0, c1, c2, c3):
   stream Z   (truncated-normal draws of tf.random.truncated_normal, core/utils.py:135)
       c0 = j        value block: the h*A values of one candidate, 4 per block, k = t*A + a, j = k // 4
       c1 = ni       GLOBAL candidate index (so results do not depend on the sharding)
-      c2 = mi       environment index
+      c2 = mi       environment index (GLOBAL: env_offset + local index when a block of environments is planned alone)
       c3 = (it << 8) | 1
       value = word k % 4 ;  u = ((w >> 9) + 0.5) * 2^-23 ;  z = sqrt(2) * erfinv(erf(sqrt(2)) * (2u - 1))
       (inverse-CDF of N(0,1) truncated to [-2, 2]; TF resamples instead -- same distribution)
   stream EPS (normal draws of tf.random.normal, core/utils.py:90)
       c0 = j        block of 4 normals of one row's D outputs, d = 4j + lane
-      c1 = row id   (mi * n + ni) * p + pi   (GLOBAL candidate index)
+      c1 = row id   (mi * n + ni) * p + pi   (GLOBAL candidate and environment indices)
       c2 = t        horizon step
       c3 = (it << 8) | 2
       Box-Muller: (w0, w1) -> r = sqrt(-2 ln u0), n0 = r cos(2 pi u1), n1 = r sin(2 pi u1); (w2, w3) -> n2, n3
@@ -72,11 +72,12 @@ def _blocks(nvals):
     return (nvals + 3) // 4
 
 
-def gen_z(seed, iters, m, n, h, A, n_offset=0, dtype=np.float32):
-    """Truncated-normal draws [iters, m, n, h, A] for candidates n_offset .. n_offset+n-1."""
+def gen_z(seed, iters, m, n, h, A, n_offset=0, dtype=np.float32, m_offset=0):
+    """Truncated-normal draws [iters, m, n, h, A] for candidates n_offset .. n_offset+n-1 of environments
+    m_offset .. m_offset+m-1 (the engine's "env_offset" option: a block of an environment-sharded decision)."""
     nb = _blocks(h * A)
     it = np.arange(iters)[:, None, None, None]
-    mi = np.arange(m)[None, :, None, None]
+    mi = (np.arange(m) + m_offset)[None, :, None, None]
     ni = (np.arange(n) + n_offset)[None, None, :, None]
     j = np.arange(nb)[None, None, None, :]
     w = philox4x32_10(j, ni, mi, (it << 8) | STREAM_Z, seed)
@@ -84,9 +85,9 @@ def gen_z(seed, iters, m, n, h, A, n_offset=0, dtype=np.float32):
     return trunc_normal_from_u(u01(words)).reshape(iters, m, n, h, A).astype(dtype)
 
 
-def gen_uniform_actions(seed, m, n, h, A, it=0, n_offset=0, dtype=np.float32):
+def gen_uniform_actions(seed, m, n, h, A, it=0, n_offset=0, dtype=np.float32, m_offset=0):
     nb = _blocks(h * A)
-    mi = np.arange(m)[:, None, None]
+    mi = (np.arange(m) + m_offset)[:, None, None]
     ni = (np.arange(n) + n_offset)[None, :, None]
     j = np.arange(nb)[None, None, :]
     w = philox4x32_10(j, ni, mi, (it << 8) | STREAM_U, seed)
@@ -94,9 +95,9 @@ def gen_uniform_actions(seed, m, n, h, A, it=0, n_offset=0, dtype=np.float32):
     return (2.0 * u01(words) - 1.0).reshape(m, n, h, A).astype(dtype)
 
 
-def gen_discrete_actions(seed, m, n, h, A, it=0, n_offset=0):
+def gen_discrete_actions(seed, m, n, h, A, it=0, n_offset=0, m_offset=0):
     nb = _blocks(h)
-    mi = np.arange(m)[:, None, None]
+    mi = (np.arange(m) + m_offset)[:, None, None]
     ni = (np.arange(n) + n_offset)[None, :, None]
     j = np.arange(nb)[None, None, :]
     w = philox4x32_10(j, ni, mi, (it << 8) | STREAM_UD, seed)
@@ -117,7 +118,7 @@ def normals_for_rows(seed, it, t, row_ids, D):
     return out.reshape(len(rid), nb * 4)[:, :D]
 
 
-def gen_eps(seed, iters, h, m, n, p, E, D, dtype=np.float32):
+def gen_eps(seed, iters, h, m, n, p, E, D, dtype=np.float32, m_offset=0):
     """Normal draws in the planner's row layout [iters, h, E, R, D], R = (p/E) m n, such that the
     particle (mi, ni, pi) -- member e = pi // (p/E), row r = (pi % (p/E)) m n + mi n + ni -- gets the
     stream-EPS values of row id (mi n + ni) p + pi."""
@@ -128,7 +129,7 @@ def gen_eps(seed, iters, h, m, n, p, E, D, dtype=np.float32):
     jq, rem = r // (m * n), r % (m * n)
     mi, ni = rem // n, rem % n
     pi = e * q + jq
-    rid = ((mi * n + ni) * p + pi).reshape(-1)
+    rid = (((mi + m_offset) * n + ni) * p + pi).reshape(-1)
     out = np.empty((iters, h, E, R, D), dtype=dtype)
     for it in range(iters):
         for t in range(h):

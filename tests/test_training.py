@@ -409,3 +409,48 @@ def test_cadm_fit_rejects_the_shapes_the_reference_asserts_on():
         bad[i] = bad[i][:, :-1]
         with pytest.raises(AssertionError):
             fit_cadm_ensemble(model, *bad, epochs=1, device="cpu")
+
+
+# ---------------------------------------------------------------------------------------------------------- optimiser state
+def test_tf_adam_matches_the_tf1_update_rule():
+    """tf.train.AdamOptimizer (TF 1.x, the reference's optimiser): lr_t = lr sqrt(1 - b2^t) / (1 - b1^t);
+    theta -= lr_t m / (sqrt(v) + eps) -- epsilon OUTSIDE the bias correction, unlike torch.optim.Adam."""
+    from cadm_b200.dynamics.training import TFAdam
+    rng = np.random.default_rng(0)
+    p0 = rng.standard_normal(7)
+    grads = [rng.standard_normal(7) * s for s in (1.0, 1e-6, 3.0, 1e-9)]       # tiny gradients: where the eps placement matters
+    p = torch.tensor(p0, dtype=torch.float64, requires_grad=True)
+    opt = TFAdam([p], lr=1e-3)
+    th, m, v = p0.copy(), np.zeros(7), np.zeros(7)
+    for t, g in enumerate(grads, 1):
+        p.grad = torch.tensor(g)
+        opt.step()
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        th = th - 1e-3 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * m / (np.sqrt(v) + 1e-8)
+        np.testing.assert_allclose(p.detach().numpy(), th, rtol=1e-13, atol=1e-15)
+    assert opt.t == 4
+
+
+def test_optimizer_state_persists_across_fit_calls():
+    """The reference creates its AdamOptimizer once, in the model constructor, so the moment slots and the step count carry
+    over from one fit() to the next on the growing dataset (mlp_ensemble_cem_dynamics.py:169).  Here: the
+    trainer is created on the first fit() and reused; replacing the parameters from outside rebuilds it."""
+    rng = np.random.default_rng(8)
+    model = _CpuModel("pendulum", E=2, H=8)
+    obs, act, nxt = _transitions(rng, model.env, 200)
+    fit_ensemble(model, obs, act, nxt, epochs=2, rng=np.random.default_rng(1), device="cpu")
+    tr = model._trainer
+    t1 = tr.optimizer.t
+    m1 = [m.clone() for m in tr.optimizer.m]
+    assert t1 > 0 and any(float(m.abs().max()) > 0 for m in m1)
+    obs2, act2, nxt2 = _transitions(rng, model.env, 100)
+    fit_ensemble(model, obs2, act2, nxt2, epochs=1, rng=np.random.default_rng(2), device="cpu")
+    assert model._trainer is tr and tr.optimizer.t > t1                     # same optimiser, the step count went on
+    # the arrays the planner reads are the trainer's tensors
+    np.testing.assert_array_equal(model._dyn["W_mu"], tr.W_mu.detach().numpy())
+    # parameters replaced from outside (load / set_params bump the version): a fresh trainer from the new arrays
+    model._dyn["W_mu"][...] = 0.0
+    model._params_version = getattr(model, "_params_version", 0) + 1
+    fit_ensemble(model, obs2, act2, nxt2, epochs=1, rng=np.random.default_rng(3), device="cpu")
+    assert model._trainer is not tr and model._trainer.optimizer.t < t1

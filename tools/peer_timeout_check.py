@@ -1,5 +1,6 @@
 """Run under torchrun on 2 GPUs: a rank that stops taking part must not hang the others on the device -- the refit kernel's
-wait for its returns slice gives up after ~2 s and the next host call raises."""
+wait for its returns slice gives up after the configured bound ("peer_timeout_ms", here 2 s; default 30 s) and
+cadm_cem_finish of THAT decision raises; "peer_clear_timeout" makes the engine usable again once the ranks are back in step."""
 import os
 import sys
 import time
@@ -22,6 +23,7 @@ planner.plan(inp["obs"], inp["init_mean"], inp["init_var"], seed=1)          # a
 torch.cuda.synchronize()
 dist.barrier()
 eng = model.engine
+eng.set_option("peer_timeout_ms", 2000)
 eng.cem_begin(inp["obs"], inp["init_mean"], inp["init_var"])
 t0 = time.time()
 raised = False
@@ -30,13 +32,27 @@ try:
         if not (rank == 1 and it == 2):
             eng.cem_rollout(it, seed=2)                                      # rank 1 "dies" in iteration 2: no slice, no flag
         eng.cem_refit(it)
-    eng.cem_finish()
-    torch.cuda.synchronize()                 # the launches are asynchronous: the report surfaces on the next call
-    eng.cem_begin(inp["obs"], inp["init_mean"], inp["init_var"])
+    eng.cem_finish()                         # waits for the refit kernels and checks their report: this decision fails
 except CadmError as e:
     raised = True
     print(f"rank {rank}: raised after {time.time() - t0:.1f} s: {e}")
 torch.cuda.synchronize()
+# both ranks re-synchronise, forget the report and plan again (rank 1 never saw a timeout: rank 0's slices all arrived)
+dist.barrier()
+eng.set_option("peer_clear_timeout", 1)
+recovered = True
+try:
+    model2, _, _ = build_model("C2", m_max=1, candidates=200 * world, rank=rank, world=world, device=f"cuda:{local}")
+    planner2 = ShardedCEMPlanner(model2.engine, fused=True)
+    planner2.plan(inp["obs"], inp["init_mean"], inp["init_var"], seed=3)
+    torch.cuda.synchronize()
+except CadmError as e:
+    recovered = False
+    print(f"rank {rank}: did not recover: {e}")
+flags = [None] * world
+dist.all_gather_object(flags, (raised, recovered))
 if rank == 0:
-    print(f"PEER_TIMEOUT_CHECK {'PASS' if raised else 'FAIL'} ({time.time() - t0:.1f} s, no hang)")
+    good = flags[0][0] and all(f[1] for f in flags)
+    print(f"PEER_TIMEOUT_CHECK {'PASS' if good else 'FAIL'} (rank 0 raised: {flags[0][0]}, recovered: {[f[1] for f in flags]}, "
+          f"{time.time() - t0:.1f} s, no hang)")
 dist.destroy_process_group()
