@@ -179,14 +179,26 @@ int run_rollout(Engine* E, RolloutParams& P, cudaStream_t s) {
             P.bpack = E->bpack_tc;
             P.bias_stride = E->bias_stride_tc;
             {
-                // batches whose 64-row tiles fit the SMs in one wave go to the swapped-operand kernel (it spreads them over
-                // 2-4x more SMs than 128-row tiles); larger ones keep the 128-row tiles of rollout_tc.cu
-                const int tiles64 = P.E * ((P.rows_per_member + 63) / 64);
+                // Which tensor-core kernel, and for the swapped-operand one how many rows per tile: the launch time is
+                // (waves of tiles over the SMs) x (time of one wave), and one wave costs about the same for every workload of the
+                // reference architecture -- measured on B200 (profiles/r2_variant_sweep.log, us per launch at h = 30):
+                //   128-row tiles (rollout_tc.cu) 570,   swapped operands (rollout_tcs.cu) 238 / 293 / 375 for 32 / 48 / 64 rows.
+                // The model reproduces the measured launch times of C2 (m = 1, 4, 10), C3 (m = 2) and C4 to 3 %.
                 const bool swapped_ok = E->Np16 <= 256 && E->NHp16 <= 128;
-                const bool swapped = E->tc_variant == 2 || (E->tc_variant == 0 && swapped_ok && tiles64 <= E->num_sms);
+                bool swapped = E->tc_variant == 2;
+                int rows_pick = E->tcs_rows;
+                if (E->tc_variant == 0 && swapped_ok) {
+                    auto waves = [&](int rows) { return (P.E * ((P.rows_per_member + rows - 1) / rows) + E->num_sms - 1) / E->num_sms; };
+                    int best = waves(128) * 570;
+                    const int cost[3] = {238, 293, 375};
+                    for (int i = 0; i < 3; ++i) {
+                        const int c = waves(32 + 16 * i) * cost[i];
+                        if (c < best) { best = c; swapped = true; if (E->tcs_rows == 0) rows_pick = 32 + 16 * i; }
+                    }
+                }
                 const int terms = E->precision == CADM_PREC_TC_3X ? 3 : 1;
                 if (swapped)
-                    CU(E, launch_rollout_tcs(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_kps, E->tcs_rows, E->tcs_skew, E->num_sms, s,
+                    CU(E, launch_rollout_tcs(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_kps, rows_pick, E->tcs_skew, E->num_sms, s,
                                              &E->kernel_name, E->trace ? E->dbg : nullptr));
                 else
                     CU(E, launch_rollout_tc(P, E->wimg, E->wimg_member_stride, terms, E->num_sms, s, &E->kernel_name,

@@ -224,7 +224,7 @@ struct RingPos {
 template <int TERMS, int NKB, int NPAD, int KPS, int KB_SPLIT>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t w16, uint32_t slot16, int nstage, RingPos& rp, uint32_t xg16,
                                            uint32_t rows, uint32_t xsbo, uint64_t* w_full, uint64_t* w_empty, uint64_t* xr,
-                                           uint64_t* acc_full, uint32_t ev) {
+                                           uint64_t* acc_full, uint32_t ev, long long* dbg = nullptr) {
     const uint32_t hi32 = (1u << 14);
     const uint64_t a_top = (uint64_t)(hi32 | (128u >> 4)) << 32;
     const uint64_t b_top = (uint64_t)(hi32 | (xsbo >> 4)) << 32;
@@ -235,6 +235,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t w16, uin
     ptx::mbar_wait(&xr[0], ev);
     if (KB_SPLIT == 0) { ptx::mbar_wait(&xr[1], ev); waited1 = true; }
     tc::fence_after_sync();
+    if (dbg) dbg[0] = clock64();
 #pragma unroll
     for (int mt = 0; mt < NMT; ++mt) {
         constexpr int R0 = NPAD < 128 ? NPAD : 128;
@@ -250,6 +251,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t w16, uin
                 ptx::mbar_wait(&xr[1], ev);
                 tc::fence_after_sync();
                 waited1 = true;
+                if (dbg) dbg[2] = clock64();
             }
             ptx::mbar_wait(&w_full[rp.slot], rp.phase);
             const uint32_t slot = w16 + rp.slot * slot16;
@@ -263,6 +265,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t w16, uin
             else issue_blocks<TERMS, 1>(d_tmem, a_hi, a_lo, b, 2u * R, rows, idesc1, idesc2, accum);
             tc::mma_commit(&w_empty[rp.slot]);
             if (s0 + kbs >= NKB) tc::mma_commit(&acc_full[mt]);
+            if (dbg && mt == 0 && s0 + kbs >= NKB) dbg[3] = clock64();
             if (++rp.slot == (uint32_t)nstage) { rp.slot = 0; rp.phase ^= 1u; }
         }
     }
@@ -409,23 +412,23 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                         long long* dbg = (dbgbase && blockIdx.x == 0 && tile == (int)blockIdx.x && t < 64) ? dbgbase + t * 64 + 32 : nullptr;
                         if (dbg) dbg[0] = clock64();
                         tcs::issue_gemm<TERMS, NKB0, 208, 4, 0>(tmem_base, w16, slot16, nstage, rp, x0_16, (uint32_t)N, (uint32_t)xsbo0, w_full,
-                                                                w_empty, xr, acc_full, ev);
+                                                                w_empty, xr, acc_full, ev, dbg ? dbg + 0 : nullptr);
                         ev ^= 1u;
                         if (dbg) { dbg[1] = clock64(); dbg[4] = dbg[1]; }
                         tcs::issue_gemm<TERMS, 13, 208, 4, 8>(tmem_base, w16, slot16, nstage, rp, xb1, (uint32_t)N, (uint32_t)xsbo, w_full,
-                                                              w_empty, xr, acc_full, ev);
+                                                              w_empty, xr, acc_full, ev, dbg ? dbg + 4 : nullptr);
                         ev ^= 1u;
                         if (dbg) { dbg[5] = clock64(); dbg[8] = dbg[5]; }
                         tcs::issue_gemm<TERMS, 13, 208, 4, 8>(tmem_base, w16, slot16, nstage, rp, x16, (uint32_t)N, (uint32_t)xsbo, w_full,
-                                                              w_empty, xr, acc_full, ev);
+                                                              w_empty, xr, acc_full, ev, dbg ? dbg + 8 : nullptr);
                         ev ^= 1u;
                         if (dbg) { dbg[9] = clock64(); dbg[12] = dbg[9]; }
                         tcs::issue_gemm<TERMS, 13, 208, 4, 8>(tmem_base, w16, slot16, nstage, rp, xb1, (uint32_t)N, (uint32_t)xsbo, w_full,
-                                                              w_empty, xr, acc_full, ev);
+                                                              w_empty, xr, acc_full, ev, dbg ? dbg + 12 : nullptr);
                         ev ^= 1u;
                         if (dbg) { dbg[13] = clock64(); dbg[16] = dbg[13]; }
                         tcs::issue_gemm<TERMS, 13, NHP, 4, 8>(tmem_base, w16, slot16, nstage, rp, x16, (uint32_t)N, (uint32_t)xsbo, w_full,
-                                                              w_empty, xr, acc_full, ev);
+                                                              w_empty, xr, acc_full, ev, dbg ? dbg + 16 : nullptr);
                         ev ^= 1u;
                         if (dbg) dbg[17] = clock64();
                     }
@@ -697,6 +700,8 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 long long* dbg = (dbgbase && blockIdx.x == 0 && ew == 2 && lane == 0 && tile == (int)blockIdx.x && t < 64) ? dbgbase + t * 64 : nullptr;
                 if (dbg) dbg[0] = clock64();
                 if (dbg) dbg[1] = clock64();
+                // per-warp detail of one step (rows 32.. of the trace buffer): for each (layer, M tile) six time stamps
+                long long* wdbg = (dbgbase && blockIdx.x == 0 && lane == 0 && tile == (int)blockIdx.x && t == T.R.h / 2) ? dbgbase + (32 + ew) * 64 : nullptr;
                 // ---------- hidden layers: accumulator -> bias + swish -> next layer's B operand ----------
 #pragma unroll 1
                 for (int l = 0; l < P.n_hidden; ++l) {
@@ -719,8 +724,10 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                             const float2 bu2 = make_float2(bu, bu);
                             uint32_t tcol = tc0 + (uint32_t)mt * kSAccStride;
                             uint32_t xo = xo_s + (uint32_t)(mt ? so1 : so0);              // 32-bit shared address: no generic-pointer conversion
+                            if (wdbg && l < 4) wdbg[(l * 2 + mt) * 6 + 0] = clock64();
                             ptx::mbar_wait(&acc_full[mt], (mt ? c1cnt : g_count) & 1u);
                             tc::fence_after_sync();
+                            if (wdbg && l < 4) wdbg[(l * 2 + mt) * 6 + 1] = clock64();
                             if (dbg && l < 4 && mt == 0) dbg[2 + 2 * l] = clock64();
                             if (active && !(dbgbits & 2)) {
                                 for (int c = cslice; c < nchunks; c += 4, tcol += 32u, xo += 4u * (uint32_t)xsbo) {
@@ -731,6 +738,7 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                                         uint32_t v1[8];
                                         tc::tmem_ld8(tcol + N, v1);
                                         tc::tmem_wait_ld();
+                                        if (wdbg && l < 4 && c == cslice) wdbg[(l * 2 + mt) * 6 + 2] = clock64();
 #pragma unroll
                                         for (int j = 0; j < 4; ++j)
                                             a[j] = tc::fadd2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])),
@@ -752,11 +760,14 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                                     }
                                 }
                             }
+                            if (wdbg && l < 4) wdbg[(l * 2 + mt) * 6 + 3] = clock64();
                             tc::fence_before_sync();
                             ptx::fence_proxy_async();
+                            if (wdbg && l < 4) wdbg[(l * 2 + mt) * 6 + 4] = clock64();
                         }
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&xr[mt]);
+                        if (wdbg && l < 4) wdbg[(l * 2 + mt) * 6 + 5] = clock64();
                         if (dbg && l < 4 && mt == 0) dbg[3 + 2 * l] = clock64();
                     }
                     ++g_count;
@@ -825,8 +836,10 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                         const float2 sc2 = make_float2(sc, sc), bj2 = make_float2(bj, bj);
                         uint32_t hd_a = hd_s + (uint32_t)((jh * (N + 4) + cslice * 8) * 4);
                         uint32_t tcol = tc0;
+                        if (wdbg) wdbg[48] = clock64();
                         ptx::mbar_wait(&acc_full[0], par0);
                         tc::fence_after_sync();
+                        if (wdbg) wdbg[49] = clock64();
                         if (dbg) dbg[10] = clock64();
                         for (int c = cslice; c < nchunks; c += 4, tcol += 32u, hd_a += 128u) {
                             uint32_t v[8];
@@ -855,7 +868,9 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                         tc::fence_before_sync();
                     }
                 }
+                if (wdbg) wdbg[50] = clock64();
                 ptx::bar_sync(1, kSEpiThreads);
+                if (wdbg) wdbg[51] = clock64();
                 if (dbg) dbg[11] = clock64();
 
                 // ---------- final epilogue: sample, next state, next step's state features -------------------------------
@@ -945,9 +960,12 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                     final_pair(r, d0, two, ca, cb, so);
                 }
                 if (dbg) dbg[13] = clock64();
+                if (wdbg) wdbg[52] = clock64();
                 if (t + 1 < P.h) publish_input();
                 if (dbg) dbg[14] = clock64();
+                if (wdbg) wdbg[53] = clock64();
                 ptx::bar_sync(1, kSEpiThreads);            // the new state is complete and visible
+                if (wdbg) wdbg[54] = clock64();
                 if (dbg) dbg[15] = clock64();
                 if (env_reward_reads_next(P.env_id)) {
                     if (et < nrows) ret += env_reward_next(P.env_id, S + et * (D + 3));

@@ -15,8 +15,8 @@ constexpr int kXsbo = (208 / 8) * 128;
 constexpr int kXbytes = (kRows / 8) * kXsbo;           // one operand half
 constexpr int kSlot = 4 * 8192;                        // 4 K blocks of [hi | lo] of a 128-row tile
 
-__host__ __device__ constexpr uint32_t idesc_sw(uint32_t rows) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | (1u << 16) | ((rows >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_sw(uint32_t rows, uint32_t M = 128u) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (1u << 16) | ((rows >> 3) << 17) | ((M >> 4) << 24);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) probe(int mode, int npairs, const unsigned char* src, long long* out) {
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads, 1) probe(int mode, int npairs, const
             const uint32_t x16 = ptx::smem_u32(xb) >> 4, w16 = ptx::smem_u32(ring) >> 4;
             const uint32_t hi32 = (1u << 14);
             const uint64_t a_top = (uint64_t)(hi32 | (128u >> 4)) << 32, b_top = (uint64_t)(hi32 | ((uint32_t)kXsbo >> 4)) << 32;
-            const uint32_t b_lbo = (128u >> 4) << 16, R = 128;
+            const uint32_t b_lbo = (128u >> 4) << 16, R = (mode & 0x200) ? 64 : 128, MM = R;      // 0x200: M = 64 tiles (64 weight rows)
             const long long t0 = clock64();
             for (int p = 0; p < npairs; p += 4) {
                 const uint32_t slot = w16 + (uint32_t)((p >> 2) & 3) * (kSlot >> 4);
@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(kThreads, 1) probe(int mode, int npairs, const
                 const uint32_t d = tmem_base + ((p >> 2) & 1) * 256u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    tc::mma_f16_ss(d, a_hi, b, idesc_sw(2 * kRows), j ? 1u : 0u);
-                    tc::mma_f16_ss(d, a_lo, b, idesc_sw(kRows), 1u);
+                    tc::mma_f16_ss(d, a_hi, b, idesc_sw(2 * kRows, MM), j ? 1u : 0u);
+                    tc::mma_f16_ss(d, a_lo, b, idesc_sw(kRows, MM), 1u);
                     a_hi += 2u * R; a_lo += 2u * R; b += 16u;
                 }
                 tc::mma_commit(&bars[1]);
@@ -157,7 +157,15 @@ int main() {
     const char* names[] = {"idle warps", "MUFU + packed FMA", "TMEM loads", "split + 2 STS.128", "LDS.128", "full epilogue chunk loop", "fence.proxy.async",
                            "FFMA", "split + 2 STS.128 + sleep"};
     const int npairs = 13 * 2 * 40;
-    for (int grid : {1, 125, 148})
+    for (int m64 = 0; m64 < 2; ++m64) {
+        cudaMemset(d, 0, 64);
+        probe<<<1, kThreads, smem_bytes>>>(m64 ? 0x200 : 0, npairs, src, d);
+        cudaDeviceSynchronize();
+        long long h[4] = {0, 0, 0, 0};
+        cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("M = %3d tiles, N = 64 + 32 per K block: %7.1f cycles per K-block pair\n", m64 ? 64 : 128, (double)h[0] / npairs);
+    }
+    for (int grid : {1})
     for (int stream = 0; stream < 2; ++stream)
         for (int m = 0; m <= 8; ++m) {
             if (grid > 1 && !(m == 0 || m == 5)) continue;
