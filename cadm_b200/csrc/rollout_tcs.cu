@@ -129,9 +129,11 @@ cudaError_t launch_pack_tcs(unsigned char* dst, const float* src, int E, int in,
 // ------------------------------------------------------------------------------------------------
 namespace tcs {
 
-// instruction descriptor: kind::f16, fp32 accumulate, A K-major, B MN-major (bit 16), M = 128, N = rows
-__host__ __device__ constexpr uint32_t idesc(uint32_t rows) {
-    return (1u << 4) | (tc::kFmtF16 << 7) | (tc::kFmtF16 << 10) | (1u << 16) | ((rows >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: kind::f16, fp32 accumulate, A K-major, B MN-major (bit 16), M = 128 (or 64), N = rows.
+// M = 64 (the heads, when they have at most 64 outputs): the 4 KB weight fetch that paces a small-N MMA halves (measured 60.5
+// cycles per K block instead of 88.7, tools/probes/m64_layout.cu); accumulator row j then lives in TMEM lane 32 (j / 16) + j % 16.
+__host__ __device__ constexpr uint32_t idesc(uint32_t rows, uint32_t M = 128u) {
+    return (1u << 4) | (tc::kFmtF16 << 7) | (tc::kFmtF16 << 10) | (1u << 16) | ((rows >> 3) << 17) | ((M >> 4) << 24);
 }
 
 struct Ring {
@@ -221,7 +223,7 @@ struct RingPos {
 // of the previous layer (0: wait for both groups up front).  Fully unrolled: per stage one mbarrier wait, 2 KPS
 // back-to-back UTCHMMAs whose descriptors differ by immediates, one or two commits -- about 30 instructions, so the lone
 // issuing thread keeps ahead of the tensor pipe (the table-driven loop needs ~150 per stage and does not).
-template <int TERMS, int NKB, int NPAD, int KPS, int KB_SPLIT>
+template <int TERMS, int NKB, int NPAD, int KPS, int KB_SPLIT, int MM = 128>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t w16, uint32_t slot16, int nstage, RingPos& rp, uint32_t xg16,
                                            uint32_t rows, uint32_t xsbo, uint64_t* w_full, uint64_t* w_empty, uint64_t* xr,
                                            uint64_t* acc_full, uint32_t ev, long long* dbg = nullptr) {
@@ -229,7 +231,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_base, uint32_t w16, uin
     const uint64_t a_top = (uint64_t)(hi32 | (128u >> 4)) << 32;
     const uint64_t b_top = (uint64_t)(hi32 | (xsbo >> 4)) << 32;
     const uint32_t b_lbo = (128u >> 4) << 16;
-    const uint32_t idesc1 = idesc(rows), idesc2 = idesc(2u * rows);
+    const uint32_t idesc1 = idesc(rows, MM), idesc2 = idesc(2u * rows, MM);
     constexpr int NMT = (NPAD + 127) / 128;
     bool waited1 = false;
     ptx::mbar_wait(&xr[0], ev);
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                                                               w_empty, xr, acc_full, ev, dbg ? dbg + 12 : nullptr);
                         ev ^= 1u;
                         if (dbg) { dbg[13] = clock64(); dbg[16] = dbg[13]; }
-                        tcs::issue_gemm<TERMS, 13, NHP, 4, 8>(tmem_base, w16, slot16, nstage, rp, x16, (uint32_t)N, (uint32_t)xsbo, w_full,
+                        tcs::issue_gemm<TERMS, 13, NHP, 4, 8, (NHP <= 64 ? 64 : 128)>(tmem_base, w16, slot16, nstage, rp, x16, (uint32_t)N, (uint32_t)xsbo, w_full,
                                                               w_empty, xr, acc_full, ev, dbg ? dbg + 16 : nullptr);
                         ev ^= 1u;
                         if (dbg) dbg[17] = clock64();
@@ -446,7 +448,9 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
             const uint32_t x0_16 = ptx::smem_u32(x0buf) >> 4;
             const uint32_t b_lbo = (128u >> 4) << 16;                           // B: LBO = 128 B between the two k-groups
             const uint32_t rows = (uint32_t)N;
-            const uint32_t idesc1 = tcs::idesc(rows), idesc2 = tcs::idesc(2u * rows);
+            const uint32_t idesc1_h = tcs::idesc(rows), idesc2_h = tcs::idesc(2u * rows);            // hidden layers: M = 128
+            const uint32_t hM = T.NHp <= 64 ? 64u : 128u;                                                // heads
+            const uint32_t idesc1_o = tcs::idesc(rows, hM), idesc2_o = tcs::idesc(2u * rows, hM);
             int my_tiles = 0;
             for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) ++my_tiles;
             long long remaining = (long long)my_tiles * P.h * nent;
@@ -474,6 +478,8 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 const uint64_t a_lo = a_top | ((slot + (uint32_t)kbs * a_step) | (R << 16));
                 const uint64_t b = e1.w == 0u ? (b_top0 | ((x0_16 + e0.z) | b_lbo)) : (b_top | ((x16 + e0.z) | b_lbo));
                 const bool skip = (dbgbits & 4) != 0;
+                const bool is_head = e1.w == (uint32_t)P.n_hidden;
+                const uint32_t idesc1 = is_head ? idesc1_o : idesc1_h, idesc2 = is_head ? idesc2_o : idesc2_h;
                 // ---- first half of the stage's MMAs
                 if (!skip) {
                     tcs::issue_blocks<TERMS, 1>(d_tmem, a_hi, a_lo, b, a_step, rows, idesc1, idesc2, e1.z);
@@ -525,7 +531,8 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
         const int nchunks = N >> 3;
         // the warps whose TMEM lane quarter holds no head output are idle in the head epilogue: they prefetch the next step's
         // actions and build its action / context features there, off the critical path
-        const int nq_head = (T.NHp + 31) >> 5;
+        const bool head64 = T.NHp <= 64;                 // heads issued as M = 64 MMAs: 16 outputs per TMEM lane quarter
+        const int nq_head = head64 ? (T.NHp + 15) >> 4 : (T.NHp + 31) >> 5;
         const bool helper = quarter >= nq_head;
         const int n_help = 128 * (4 - nq_head);                                  // 0 when the heads fill all four quarters
         const int ht = ((quarter - nq_head) + (4 - nq_head) * cslice) * 32 + lane;    // index among the helper threads
@@ -829,8 +836,9 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
                 {
                     const uint32_t par0 = g_count & 1u;
                     ++g_count;
-                    if (quarter * 32 < T.NHp) {
-                        const int jh = qlane;
+                    if (quarter < nq_head) {
+                        const bool lane_ok = !head64 || lane < 16;
+                        const int jh = head64 ? quarter * 16 + (lane & 15) : qlane;
                         const float bj = jh < T.NHp ? bias[P.n_hidden * T.Np + jh] : 0.f;
                         const float sc = 1.0f / (tc::kWScale * tc::kActScale);
                         const float2 sc2 = make_float2(sc, sc), bj2 = make_float2(bj, bj);
@@ -858,7 +866,7 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) a[j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                             }
-                            if (jh < T.NHp) {
+                            if (jh < T.NHp && lane_ok) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) a[j] = tc::ffma2(a[j], sc2, bj2);
                                 ptx::sts128(hd_a, __float_as_uint(a[0].x), __float_as_uint(a[0].y), __float_as_uint(a[1].x), __float_as_uint(a[1].y));
