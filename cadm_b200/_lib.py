@@ -22,6 +22,18 @@ class CadmConfig(C.Structure):
     ]
 
 
+# must mirror struct CadmTrainConfig in include/cadm_b200.h
+class CadmTrainConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("env_id", C.c_int32), ("obs_dim", C.c_int32), ("proc_obs_dim", C.c_int32),
+        ("act_dim", C.c_int32), ("ctx_dim", C.c_int32), ("hist_len", C.c_int32), ("hidden", C.c_int32),
+        ("n_hidden", C.c_int32), ("enc_hidden", C.c_int32 * 3), ("ensemble", C.c_int32), ("deterministic", C.c_int32),
+        ("has_back", C.c_int32), ("back_coeff", C.c_float), ("weight_decay_coeff", C.c_float), ("learning_rate", C.c_float),
+        ("weight_decays", C.c_float * 8), ("context_weight_decays", C.c_float * 4),
+        ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("adam_eps", C.c_float),
+    ]
+
+
 ENV_IDS = {"halfcheetah": 0, "cripple_halfcheetah": 0, "ant": 1, "slim_humanoid": 2, "cartpole": 3, "pendulum": 4}
 PRECISIONS = {"fp32": 0, "tc3x": 1, "tc1x": 2}
 CTX_LAYOUTS = {"reference": 0, "matched": 1}
@@ -68,6 +80,19 @@ SIGNATURES = {
     "cadm_kernel_name": (C.c_char_p, [_P]),
     "cadm_set_timing": (C.c_int, [_P, C.c_int32]),
     "cadm_last_rollout_ms": (C.c_float, [_P]),
+    # fit() on the device (csrc/trainer.cu)
+    "cadm_train_create": (C.c_int, [C.POINTER(CadmTrainConfig), C.POINTER(_P)]),
+    "cadm_train_destroy": (C.c_int, [_P]),
+    "cadm_train_last_error": (C.c_char_p, [_P]),
+    "cadm_train_param_count": (C.c_int64, [_P]),
+    "cadm_train_launch_count": (C.c_int64, [_P]),
+    "cadm_train_set_params": (C.c_int, [_P, C.c_void_p, C.c_int64]),
+    "cadm_train_get_params": (C.c_int, [_P, C.c_void_p, C.c_int64]),
+    "cadm_train_get_grads": (C.c_int, [_P, C.c_void_p, C.c_int64]),
+    "cadm_train_adam_state": (C.c_int, [_P, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "cadm_train_set_norm": (C.c_int, [_P, C.POINTER(C.c_void_p), C.c_int32]),
+    "cadm_train_set_dataset": (C.c_int, [_P, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
+    "cadm_train_step": (C.c_int, [_P, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

@@ -4,10 +4,13 @@ The training graphs of cadm/dynamics/mlp_ensemble_cem_dynamics.py:86-170 and mlp
 (losses) and core/utils.py:43-97, 251-372, 569-624 (forward on the bootstrap batch) restated with PyTorch autograd: the
 ensemble MLP on [E, B, .] batches, Gaussian NLL with the soft-bounded log-variance, the max/min-logvar regulariser,
 per-layer L2 terms, Adam; for CaDM also the context encoder trained end to end through the forward (and backward) model,
-the deterministic backward model weighted by back_coeff, and the flattening of the future_length-step samples.  PyTorch is used here the way the reference uses
-TensorFlow -- library GEMMs and autograd on whatever device the tensors live on (the B200 in production, the CPU in the
-tests); the hand-written CUDA of this package is the planner.  After training the arrays are handed back to the model,
-which repacks them for the engine (cadm_plan_set_weights).
+the deterministic backward model weighted by back_coeff, and the flattening of the future_length-step samples.
+
+Two trainers implement the step: on a CUDA device fit() runs the hand-written kernels of csrc/trainer.cu through
+native_trainer.NativeTrainer (dataset resident in HBM, minibatches as index matrices, no torch on the path); the autograd
+classes below are the restatement the kernels are checked against (and what a CPU-only caller gets).  The loops around them
+are shared.  After training the arrays are handed back to the model, which repacks them for the engine
+(cadm_plan_set_weights).
 """
 import numpy as np
 import torch
@@ -62,6 +65,27 @@ def model_trainer(model, make):
         tr = make()
         model._trainer = tr
     return tr
+
+
+def _is_cuda(device):
+    return device is not None and torch.device(device).type == "cuda"
+
+
+def make_trainer(model, device):
+    """The trainer of `model` on `device`: the hand-written kernels on a CUDA device, the autograd restatement otherwise."""
+    cadm = getattr(model, "_enc", None) is not None
+    if _is_cuda(device):
+        from .native_trainer import NativeTrainer
+        return NativeTrainer(model._enc if cadm else None, model._dyn, model._back if cadm else None, model.env_name,
+                             model.obs_space_dims, model.proc_obs_space_dims, model.action_space_dims,
+                             getattr(model, "history_length", 0), model.deterministic, model.weight_decays,
+                             getattr(model, "context_weight_decays", (0.0,)), model.weight_decay_coeff,
+                             getattr(model, "back_coeff", 0.0), model.learning_rate, device=device)
+    if cadm:
+        return CaDMTrainer(model._enc, model._dyn, model._back, model.env_name, model.deterministic, model.weight_decays,
+                           model.context_weight_decays, model.weight_decay_coeff, model.back_coeff, model.learning_rate, device=device)
+    return EnsembleNLLTrainer(model._dyn, model.env_name, model.deterministic, model.weight_decays, model.weight_decay_coeff,
+                              model.learning_rate, device=device)
 
 
 def trainer_done(model):
@@ -150,6 +174,16 @@ class EnsembleNLLTrainer:
         out = self.losses(bs_obs, bs_act, bs_delta, stats)
         return float(out["mse_loss"]), float(out["recon_loss"])
 
+    # index-based interface shared with native_trainer.NativeTrainer: the datasets are handed over once per fit()
+    def begin_fit(self, train, valid, stats):
+        self._data, self._stats = (train, valid), stats
+
+    def train_step_idx(self, idx):
+        return self.train_step(*[a[idx] for a in self._data[0]], self._stats)
+
+    def evaluate_idx(self, idx, which=1):
+        return self.evaluate(*[a[idx] for a in self._data[which]], self._stats)
+
     def export(self, dyn):
         """Write the trained values back into the model's arrays (in place, float32)."""
         g = lambda p: p.detach().to("cpu", torch.float32).numpy()
@@ -210,8 +244,8 @@ def fit_ensemble(model, obs, act, obs_next, epochs=1000, valid_split_ratio=None,
 
     if device is None:
         device = model.engine.device if getattr(model, "engine", None) is not None else "cpu"
-    trainer = model_trainer(model, lambda: EnsembleNLLTrainer(model._dyn, model.env_name, model.deterministic, model.weight_decays,
-                                                              model.weight_decay_coeff, model.learning_rate, device=device))
+    trainer = model_trainer(model, lambda: make_trainer(model, device))
+    trainer.begin_fit((train_obs, train_act, train_delta), (valid_obs, valid_act, valid_delta), stats)
     rolling, rolling_prev = None, None
     epoch = -1
     for epoch in range(epochs):
@@ -219,11 +253,11 @@ def fit_ensemble(model, obs, act, obs_next, epochs=1000, valid_split_ratio=None,
         bootstrap_idx = shuffle_rows(bootstrap_idx)
         for batch_num in range(int(np.ceil(bootstrap_idx.shape[-1] / model.batch_size))):
             idx = bootstrap_idx[:, batch_num * model.batch_size:(batch_num + 1) * model.batch_size]
-            m_, r_ = trainer.train_step(train_obs[idx], train_act[idx], train_delta[idx], stats)
+            m_, r_ = trainer.train_step_idx(idx)
             mse_losses.append(m_)
             recon_losses.append(r_)
         if n_valid_split > 0:
-            v_mse, v_recon = trainer.evaluate(valid_obs[valid_idx], valid_act[valid_idx], valid_delta[valid_idx], stats)
+            v_mse, v_recon = trainer.evaluate_idx(valid_idx)
             if verbose:
                 log("Training DynamicsModel - finished epoch %i --[Training] mse loss: %.4f  recon loss:  %.4f "
                     "[Validation] mse loss: %.4f  recon loss:  %.4f" % (epoch, np.mean(mse_losses), np.mean(recon_losses), v_mse, v_recon))
@@ -333,6 +367,15 @@ class CaDMTrainer:
         out = self.losses(*batch_and_stats)
         return float(out["mse_loss"]), float(out["back_mse_loss"]), float(out["recon_loss"])
 
+    def begin_fit(self, train, valid, stats):
+        self._data, self._stats = (train, valid), stats
+
+    def train_step_idx(self, idx):
+        return self.train_step(*[a[idx] for a in self._data[0]], self._stats)
+
+    def evaluate_idx(self, idx, which=1):
+        return self.evaluate(*[a[idx] for a in self._data[which]], self._stats)
+
     def export(self, enc, dyn, back):
         g = lambda p: p.detach().to("cpu", torch.float32).numpy()
         for dst, src in zip(enc["W"], self.enc_W):
@@ -412,9 +455,8 @@ def fit_cadm_ensemble(model, obs, act, obs_next, cp_obs, cp_act, future_bool, ep
 
     if device is None:
         device = model.engine.device if getattr(model, "engine", None) is not None else "cpu"
-    trainer = model_trainer(model, lambda: CaDMTrainer(model._enc, model._dyn, model._back, model.env_name, model.deterministic,
-                                                       model.weight_decays, model.context_weight_decays, model.weight_decay_coeff,
-                                                       model.back_coeff, model.learning_rate, device=device))
+    trainer = model_trainer(model, lambda: make_trainer(model, device))
+    trainer.begin_fit(train, valid, stats)
     rolling, rolling_prev = None, None
     epoch = -1
     mse_losses, back_mse_losses, recon_losses = [], [], []
@@ -423,12 +465,12 @@ def fit_cadm_ensemble(model, obs, act, obs_next, cp_obs, cp_act, future_bool, ep
         bootstrap_idx = shuffle_rows(bootstrap_idx)
         for batch_num in range(int(np.ceil(bootstrap_idx.shape[-1] / model.batch_size))):
             idx = bootstrap_idx[:, batch_num * model.batch_size:(batch_num + 1) * model.batch_size]
-            m_, b_, r_ = trainer.train_step(*[a[idx] for a in train], stats)
+            m_, b_, r_ = trainer.train_step_idx(idx)
             mse_losses.append(m_)
             back_mse_losses.append(b_)
             recon_losses.append(r_)
         if n_valid_split > 0:
-            v_mse, v_back, v_recon = trainer.evaluate(*[a[valid_idx] for a in valid], stats)
+            v_mse, v_back, v_recon = trainer.evaluate_idx(valid_idx)
             if verbose:
                 log("Training DynamicsModel - finished epoch %i --[Training] mse loss: %.4f  back mse loss: %.4f  recon loss:  %.4f "
                     "[Validation] mse loss: %.4f  back mse loss: %.4f  recon loss:  %.4f"

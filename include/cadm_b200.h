@@ -267,6 +267,69 @@ const char* cadm_kernel_name(void* handle);
 int   cadm_set_timing(void* handle, int32_t on);
 float cadm_last_rollout_ms(void* handle);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * fit() on the device.  The training graph of the reference -- ensemble dynamics MLP, Gaussian NLL with
+ * the soft-bounded log-variance, max / min logvar regulariser, per-layer L2 (mlp_ensemble_cem_dynamics.py:86-170,
+ * core/utils.py:43-97, 635-647); for CaDM the context encoder trained end to end through the forward model and the
+ * deterministic backward model weighted by back_coeff (mlp_cadm_ensemble_cem_dynamics.py:108-317, core/utils.py:251-372,
+ * 569-624); tf.train.AdamOptimizer -- as hand-written forward / backward / Adam kernels (csrc/trainer.cu).  What the reference
+ * feeds per minibatch through sess.run (mlp_ensemble_cem_dynamics.py:262-283, mlp_cadm_ensemble_cem_dynamics.py:478-527)
+ * is here an index matrix into a dataset that stays on the device for the whole fit().
+ *
+ * Flat parameter vector (cadm_train_set_params / get_params / get_grads / adam_state), every tensor row-major:
+ *   encoder (ctx_dim > 0):  for each layer  W [E, in, out], b [E, out]      ((D + A) K -> enc_hidden... -> C; relu, linear out)
+ *   forward model:          for each hidden layer  W [E, in, H], b [E, H]   (in = P + A + C for the first; swish)
+ *                           heads  W [E, H, 2 D] = [output_mu | output_logvar] column blocks, b [E, 2 D]
+ *   max_logvar [D], min_logvar [D]
+ *   backward model (has_back): hidden layers and heads like the forward model
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct CadmTrainConfig {
+    int32_t struct_size;          /* sizeof(CadmTrainConfig) */
+    int32_t env_id;               /* CADM_ENV_*: obs_preproc applied to the gathered observations */
+    int32_t obs_dim;              /* D */
+    int32_t proc_obs_dim;         /* P */
+    int32_t act_dim;              /* A */
+    int32_t ctx_dim;              /* C; 0 = PE-TS / vanilla model (no encoder) */
+    int32_t hist_len;             /* K */
+    int32_t hidden;               /* H */
+    int32_t n_hidden;
+    int32_t enc_hidden[3];        /* reference: 256, 128, 64 (0 ends the list) */
+    int32_t ensemble;             /* E */
+    int32_t deterministic;        /* 1: loss = mse (vanilla DM) */
+    int32_t has_back;             /* backward model present (back_coeff > 0; CaDM only) */
+    float   back_coeff;
+    float   weight_decay_coeff;
+    float   learning_rate;
+    float   weight_decays[8];     /* hidden layer i: [i]; both heads: [n_hidden]  (core/utils.py:46-69) */
+    float   context_weight_decays[4];   /* encoder hidden layer i: [i]; output layer: [number of hidden layers] */
+    float   adam_beta1, adam_beta2, adam_eps;   /* tf.train.AdamOptimizer defaults: 0.9, 0.999, 1e-8 */
+} CadmTrainConfig;
+
+int         cadm_train_create(const CadmTrainConfig* cfg, void** handle);
+int         cadm_train_destroy(void* handle);
+const char* cadm_train_last_error(const void* handle);
+int64_t     cadm_train_param_count(void* handle);
+int64_t     cadm_train_launch_count(void* handle);
+int cadm_train_set_params(void* handle, const float* flat_host, int64_t n);
+int cadm_train_get_params(void* handle, float* flat_host, int64_t n);
+/* gradient of the last training step, same layout (tests compare it with autograd and finite differences) */
+int cadm_train_get_grads(void* handle, float* flat_host, int64_t n);
+/* Adam slots m, v and step count t: set != 0 uploads, set == 0 downloads.  They live in the handle, so they persist across
+ * fit() calls as long as the handle does (the reference creates the optimiser once, in the constructor). */
+int cadm_train_adam_state(void* handle, int32_t set, float* m_host, float* v_host, int64_t n, int64_t* t_inout);
+/* get_normalization_stats() order: obs mean/std [P], act mean/std [A], delta mean/std [D], cp_obs mean/std [D K],
+ * cp_act mean/std [A K], back_delta mean/std [D]; count = 6 (PE-TS), 10 (CaDM) or 12 (CaDM with backward model). */
+int cadm_train_set_norm(void* handle, const float* const* stats_host, int32_t count);
+/* Uploads a dataset: which = 0 training rows, 1 validation rows.  obs / obs_next / delta / back_delta [rows, D], act [rows, A],
+ * cp_obs [rows, D K], cp_act [rows, A K]; the arguments the model does not use may be NULL. */
+int cadm_train_set_dataset(void* handle, int32_t which, int64_t rows, const float* obs_host, const float* act_host,
+                           const float* delta_host, const float* obs_next_host, const float* back_delta_host,
+                           const float* cp_obs_host, const float* cp_act_host);
+/* One minibatch: idx_host [E, B] rows of dataset `which` (member e trains on its own bootstrap rows).  train != 0: forward,
+ * backward, one Adam step; train == 0: losses only.  losses_host [4] = mse_loss, recon_loss, back_mse_loss, mu_loss
+ * (mlp_ensemble_cem_dynamics.py:150-167, mlp_cadm_ensemble_cem_dynamics.py:266-314).  Synchronises. */
+int cadm_train_step(void* handle, int32_t which, const int32_t* idx_host, int32_t B, int32_t train, float* losses_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,39 @@ def test_config_struct_matches_header(tmp_path):
     assert vals[1:] == [getattr(CadmConfig, f).offset for f in fields]
 
 
+def test_train_config_struct_matches_header(tmp_path):
+    """sizeof / field offsets of CadmTrainConfig (fit() on the device) as seen by gcc equal the ctypes mirror."""
+    from cadm_b200._lib import CadmTrainConfig
+    fields = [f[0] for f in CadmTrainConfig._fields_]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "cadm_b200.h"\nint main(){printf("%zu", sizeof(CadmTrainConfig));' + \
+        "".join(f'printf(" %zu", offsetof(CadmTrainConfig, {f}));' for f in fields) + "return 0;}"
+    c = tmp_path / "t.c"
+    c.write_text(prog)
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert vals[0] == ctypes.sizeof(CadmTrainConfig)
+    assert vals[1:] == [getattr(CadmTrainConfig, f).offset for f in fields]
+
+
+def test_trainer_has_no_cpu_fallback(lib):
+    """cadm_train_create validates its configuration and, without a CUDA device, fails instead of training on the host."""
+    import torch
+    from cadm_b200._lib import CadmTrainConfig
+    cfg = CadmTrainConfig()
+    h = ctypes.c_void_p()
+    assert lib.cadm_train_create(ctypes.byref(cfg), ctypes.byref(h)) == -1         # struct_size not set
+    assert b"struct_size" in lib.cadm_train_last_error(None)
+    cfg.struct_size = ctypes.sizeof(CadmTrainConfig)
+    cfg.obs_dim, cfg.proc_obs_dim, cfg.act_dim, cfg.hidden, cfg.n_hidden, cfg.ensemble = 18, 18, 6, 200, 4, 5
+    cfg.has_back = 1                                                               # backward model without a context encoder
+    assert lib.cadm_train_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    cfg.has_back = 0
+    if not torch.cuda.is_available():
+        assert lib.cadm_train_create(ctypes.byref(cfg), ctypes.byref(h)) == -2     # CADM_ERR_CUDA
+        assert b"no CPU fallback" in lib.cadm_train_last_error(None)
+
+
 def test_create_rejects_bad_config(lib):
     from cadm_b200.engine import PlannerConfig
     cfg = PlannerConfig(particles=7, ensemble=5).to_c()
