@@ -18,6 +18,8 @@ __device__ __forceinline__ float cem_action_value(float mean, float var, float z
 
 
 __global__ void sample_actions_kernel(const SampleParams S) {
+    griddep_launch();
+    griddep_wait();                 // mean / var come from the previous refit, which also still reads the actions written here
     const int nb = (S.hA + 3) / 4;
     const long long total = (long long)S.m * S.n_local * nb;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -53,8 +55,7 @@ cudaError_t launch_sample_actions(const SampleParams& S, cudaStream_t stream) {
     const long long total = (long long)S.m * S.n_local * ((S.hA + 3) / 4);
     const int threads = 256;
     const int blocks = (int)min((total + threads - 1) / threads, (long long)148 * 8);
-    sample_actions_kernel<<<max(blocks, 1), threads, 0, stream>>>(S);
-    return cudaGetLastError();
+    return launch_chain(sample_actions_kernel, dim3(max(blocks, 1)), dim3(threads), 0, stream, S);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -114,6 +115,8 @@ __global__ void __launch_bounds__(1024, 1) refit_kernel(const RefitParams R) {
     const int hA = R.h * R.A;
     float* el = reinterpret_cast<float*>(keys + R.npad);
     const float* returns_buf = R.returns_buf;
+    griddep_launch();
+    griddep_wait();                 // the rollout's particle returns
     if (R.peers != nullptr) {
         // Fused all-gather over peer memory (multi-GPU): this CTA averages the particle returns of ITS environment's local
         // candidates (the fixed summation order of core/utils.py:170, so the value does not depend on the sharding), stores
@@ -296,8 +299,7 @@ cudaError_t launch_refit(RefitParams R, cudaStream_t stream) {
         g_refit_smem = (int)smem;
     }
     const int threads = 1024;      // the elite gather and the per-coordinate reductions want every thread the CTA can have
-    refit_kernel<<<R.m, threads, smem, stream>>>(R);
-    return cudaGetLastError();
+    return launch_chain(refit_kernel, dim3(R.m), dim3(threads), smem, stream, R);
 }
 
 // random shooting: gather the first action of the best candidate (core/utils.py:239-245)

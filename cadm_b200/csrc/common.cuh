@@ -64,6 +64,34 @@ struct RolloutParams {
 __host__ __device__ inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The three kernels of a CEM iteration (sample_actions -> rollout -> refit) are short
+// next to their launch latency and strictly ordered; launched with cudaLaunchAttributeProgrammaticStreamSerialization the next
+// kernel's CTAs become resident -- and run whatever does not depend on its predecessor: barrier / TMEM set-up, bias and
+// feature tables, the first weight stages -- while the predecessor is still running, and block in griddep_wait() until the
+// predecessor's grid has completed and its writes are visible.  Rule for every kernel of the chain: nothing the predecessor
+// writes is read, and nothing it reads is written, before griddep_wait().  Without the launch attribute both calls are no-ops.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern bool g_pdl;      // engine.cu: CADM_PDL=0 or cadm_set_option("pdl", 0) turns the attribute off (A/B, debugging)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // environment closures (see include/cadm_b200.h CADM_ENV_* for the reference lines)
 // ---------------------------------------------------------------------------------------------
 

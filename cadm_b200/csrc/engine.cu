@@ -1,6 +1,7 @@
 // C ABI of the engine (include/cadm_b200.h): handle, device buffers, weight packing, launch sequencing.
 // No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -10,6 +11,11 @@
 #include "kernels.cuh"
 
 using namespace cadm;
+
+namespace cadm {
+// programmatic dependent launch of the sample -> rollout -> refit chain (common.cuh); CADM_PDL=0 or option "pdl" turn it off
+bool g_pdl = [] { const char* v = getenv("CADM_PDL"); return !(v && v[0] == '0'); }();
+}  // namespace cadm
 
 namespace {
 
@@ -922,6 +928,8 @@ int cadm_set_option(void* handle, const char* name, int32_t value) {
         if (E->peer_timeout_host) *reinterpret_cast<volatile int*>(E->peer_timeout_host) = 0;
     } else if (k == "trace") {
         E->trace = value != 0;
+    } else if (k == "pdl") {
+        cadm::g_pdl = value != 0;              // process-wide: programmatic dependent launch of the CEM kernel chain
     } else if (k == "tcs_skew") {
         if (value < 0) return fail(E, CADM_ERR_ARG, "tcs_skew must be non-negative (bits 20+ are diagnostic switches)");
         E->tcs_skew = value;

@@ -88,6 +88,8 @@ __device__ __forceinline__ void gemm_stream(float (&acc)[RT][CT], const float* _
 
 template <int TR>
 __global__ void __launch_bounds__(kThreads, 1) rollout_f32_kernel(const __grid_constant__ RolloutParams P) {
+    griddep_launch();
+    griddep_wait();            // programmatic dependent launch (common.cuh): the candidates' actions come from the kernel before
     constexpr int RT = TR / 8;   // rows per thread
     extern __shared__ __align__(128) unsigned char smem[];
     const SmemLayoutF32 L = smem_layout_f32(TR, P.D, P.n_hidden, P.Hp, P.NHp);
@@ -400,7 +402,7 @@ cudaError_t launch_rollout_f32(RolloutParams P, int num_sms, cudaStream_t stream
             g_smem_set[1] = 1;
         }
         if (name) *name = "rollout_f32_kernel<64>";
-        rollout_f32_kernel<64><<<grid, block, L.total, stream>>>(P);
+        err = launch_chain(rollout_f32_kernel<64>, dim3(grid), dim3(block), L.total, stream, P);
     } else {
         if (!g_smem_set[0]) {
             err = cudaFuncSetAttribute(rollout_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -408,9 +410,9 @@ cudaError_t launch_rollout_f32(RolloutParams P, int num_sms, cudaStream_t stream
             g_smem_set[0] = 1;
         }
         if (name) *name = "rollout_f32_kernel<32>";
-        rollout_f32_kernel<32><<<grid, block, L.total, stream>>>(P);
+        err = launch_chain(rollout_f32_kernel<32>, dim3(grid), dim3(block), L.total, stream, P);
     }
-    return cudaGetLastError();
+    return err != cudaSuccess ? err : cudaGetLastError();
 }
 
 }  // namespace cadm

@@ -191,6 +191,8 @@ struct TcParams {
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_constant__ TcParams T) {
+    griddep_launch();
+    griddep_wait();            // programmatic dependent launch (common.cuh): the candidates' actions come from the kernel before
     const RolloutParams& P = T.R;
     extern __shared__ __align__(1024) unsigned char smem[];
     const TcSmem L = tc_smem_layout(P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, T.stages);
@@ -673,8 +675,7 @@ cudaError_t launch_rollout_tc(RolloutParams P, const unsigned char* wimg, long l
     }
     if (name) *name = terms == 3 ? "rollout_tc_kernel(fp16 hi/lo x3)" : "rollout_tc_kernel(f16 x1)";
     const int grid = min(T.total_tiles, num_sms);
-    rollout_tc_kernel<<<grid, kTcThreads, L.total, stream>>>(T);
-    return cudaGetLastError();
+    return launch_chain(rollout_tc_kernel, dim3(grid), dim3(kTcThreads), L.total, stream, T);
 }
 
 

@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const int nent = T.nent;
+    griddep_launch();                              // the refit kernel may become resident; it blocks until this grid is complete
     if (T.skew > 0) {                              // de-phase the CTAs' weight-stream bursts (see launch_rollout_tcs)
         const long long until = clock64() + (long long)(blockIdx.x % 8) * T.skew;
         while (clock64() < until) __nanosleep(200);
@@ -648,6 +649,10 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
             for (int i = et; i < 2 * N * A; i += kSEpiThreads) act_s[i] = 0.f;   // rows >= nrows stay finite
             ptx::bar_sync(1, kSEpiThreads);
             if (P.env_id == CADM_ENV_HALFCHEETAH && et < N) sincosf(S[et * (D + 3) + 2], &S[et * (D + 3) + D + 1], &S[et * (D + 3) + D + 2]);
+            // everything above reads inputs that are constant over the decision; the candidates' actions come from the kernel
+            // launched just before this one (sample_actions), and the particle returns written at the end are still being read
+            // by the refit before it: wait for the predecessor grid here (programmatic dependent launch, common.cuh)
+            griddep_wait();
             prefetch_actions(0, et, kSEpiThreads);
             tcs::cp_async_wait_all();
             ptx::bar_sync(1, kSEpiThreads);
@@ -1094,15 +1099,16 @@ cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long 
     const bool diag = T.debug != 0 || T.dbg != nullptr;
 #define CADM_TCS_LAUNCH(TE, K0, HP)                                                                  \
     do {                                                                                             \
-        if (diag) rollout_tcs_kernel<TE, K0, HP, true><<<grid, kSThreads, L.total, stream>>>(T);    \
-        else rollout_tcs_kernel<TE, K0, HP, false><<<grid, kSThreads, L.total, stream>>>(T);         \
+        if (diag) le = launch_chain(rollout_tcs_kernel<TE, K0, HP, true>, dim3(grid), dim3(kSThreads), L.total, stream, T);    \
+        else le = launch_chain(rollout_tcs_kernel<TE, K0, HP, false>, dim3(grid), dim3(kSThreads), L.total, stream, T);         \
     } while (0)
+    cudaError_t le = cudaSuccess;
     if (!spec) { if (terms == 3) CADM_TCS_LAUNCH(3, 0, 0); else CADM_TCS_LAUNCH(1, 0, 0); }
     else if (T.nkb0 == 2) { if (terms == 3) CADM_TCS_LAUNCH(3, 2, 48); else CADM_TCS_LAUNCH(1, 2, 48); }
     else if (T.NHp == 48) { if (terms == 3) CADM_TCS_LAUNCH(3, 3, 48); else CADM_TCS_LAUNCH(1, 3, 48); }
     else { if (terms == 3) CADM_TCS_LAUNCH(3, 3, 64); else CADM_TCS_LAUNCH(1, 3, 64); }
 #undef CADM_TCS_LAUNCH
-    return cudaGetLastError();
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
