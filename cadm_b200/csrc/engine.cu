@@ -35,7 +35,7 @@ struct Engine {
     // tensor-core image (hi/lo split, UMMA layout) and its 16-padded biases
     unsigned char* wimg = nullptr;
     unsigned char* wimg_s = nullptr;   // same weights packed for the swapped-operand kernel (rollout_tcs.cu)
-    int tc_variant = 0;                // 0 auto, 1 row tiles (rollout_tc.cu), 2 swapped operands (rollout_tcs.cu)
+    int tc_variant = 0;                // 0 auto, 1 row tiles (rollout_tc.cu), 2 swapped operands (rollout_tcs.cu), 3 CTA pairs (rollout_tcp.cu)
     int tcs_rows = 0;                  // rows per tile of the swapped kernel (0 = pick)
     bool trace = false;                // clock64 phase trace of CTA 0 (perturbs that CTA: off unless asked for)
     int tcs_skew = 0;                  // start-delay step (cycles) that de-phases the CTAs of the swapped kernel
@@ -203,7 +203,10 @@ int run_rollout(Engine* E, RolloutParams& P, cudaStream_t s) {
                     }
                 }
                 const int terms = E->precision == CADM_PREC_TC_3X ? 3 : 1;
-                if (swapped)
+                if (E->tc_variant == 3) {
+                    if (!tcp_supported(P, E->tcs_kps)) return fail(E, CADM_ERR_UNSUPPORTED, "tc_variant 3 (CTA pairs) covers the reference architecture only");
+                    CU(E, launch_rollout_tcp(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_rows, E->num_sms, s, &E->kernel_name, E->trace ? E->dbg : nullptr));
+                } else if (swapped)
                     CU(E, launch_rollout_tcs(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_kps, rows_pick, E->tcs_skew, E->num_sms, s,
                                              &E->kernel_name, E->trace ? E->dbg : nullptr));
                 else
@@ -906,7 +909,7 @@ int cadm_set_option(void* handle, const char* name, int32_t value) {
     if (!E || !name) return CADM_ERR_ARG;
     const std::string k(name);
     if (k == "tc_variant") {
-        if (value < 0 || value > 2) return fail(E, CADM_ERR_ARG, "tc_variant must be 0 (auto), 1 (row tiles) or 2 (swapped operands)");
+        if (value < 0 || value > 3) return fail(E, CADM_ERR_ARG, "tc_variant must be 0 (auto), 1 (row tiles), 2 (swapped operands) or 3 (CTA pairs)");
         E->tc_variant = value;
     } else if (k == "tcs_rows") {
         if (value < 0 || value > 64 || value % 16) return fail(E, CADM_ERR_ARG, "tcs_rows must be 0 (pick) or a multiple of 16 up to 64");

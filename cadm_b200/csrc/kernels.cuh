@@ -87,6 +87,10 @@ cudaError_t launch_pack_tc(unsigned char* dst, const float* src, int E, int in, 
                            long long member_stride, long long layer_off, int clear, cudaStream_t stream);
 cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long long wimg_member_stride, int terms, int kps,
                                int rows_override, int skew, int num_sms, cudaStream_t stream, const char** name, long long* dbg);
+// CTA-pair variant of the swapped-operand kernel (rollout_tcp.cu); reads the weight image of rollout_tcs.cu packed with kps = 4
+bool tcp_supported(const RolloutParams& P, int kps);
+cudaError_t launch_rollout_tcp(RolloutParams P, const unsigned char* wimg, long long wimg_member_stride, int terms, int rows_override,
+                               int num_sms, cudaStream_t stream, const char** name, long long* dbg);
 cudaError_t launch_pack_tcs(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad, int kps,
                             long long member_stride, long long layer_off, int clear, cudaStream_t stream);
 cudaError_t launch_tcs_gemm_selftest(const float* X, const unsigned char* wimg, int rows, int K, int Nout, int kps, int terms,

@@ -63,6 +63,53 @@ __device__ __forceinline__ void sts16(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory");
 }
 
+// ---- thread-block clusters: rank, barrier, distributed shared memory -------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `saddr` (a shared::cta address of THIS CTA) in the CTA of rank `cta`
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void sts128_cluster(uint32_t caddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts32_cluster(uint32_t caddr, uint32_t v) {
+    asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(caddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts16_cluster(uint32_t caddr, uint32_t v) {
+    asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(caddr), "h"((unsigned short)v) : "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster (release at cluster scope: the stores above are visible to its waiters)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+// wait with acquire at cluster scope (the arrivals may come from the other CTA of the pair)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait_cluster(bar, parity)) {
+    }
+}
+// generic-proxy writes (of any CTA of the cluster) -> async-proxy reads (tcgen05.mma operands), all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -122,6 +169,14 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
 // mbarrier arrive when all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
+}
+
+// the same arrive on the mbarrier at this shared-memory offset in EVERY CTA of `cta_mask` (a CTA pair hands "my half of the
+// layer is done" to both halves with one instruction)
+__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(ptx::smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
 }
 
 // ---- TMEM -> registers: 32 lanes x 32 bit, 16 / 8 consecutive columns --------------------------

@@ -32,6 +32,8 @@ KERNELS = {
     "tiles128": ("tc3x", "1", None),
     "swapped64": ("tc3x", "2", "64"),
     "swapped32": ("tc3x", "2", "32"),
+    "pairs32": ("tc3x", "3", "32"),
+    "pairs64": ("tc3x", "3", "64"),
 }
 
 
@@ -165,10 +167,10 @@ def test_c4_full_decision():
     decision (context encoder, odd-iteration context pairing, 5 x 30 steps, top-50 of 1000, refit) on every kernel."""
     from cadm_b200.synth import synthetic_inputs
     ref = None
-    for kernel in ("tiles128", "swapped64", "fp32"):
+    for kernel in ("tiles128", "swapped64", "pairs64", "fp32"):
         model, env, cfg = _build("C4", kernel, m_max=1)
         assert cfg["candidates"] == 1000 and cfg["horizon"] == 30
-        if kernel != "fp32":
+        if kernel in ("tiles128", "swapped64"):
             assert _tiles(cfg, 1, 1000, 128 if kernel == "tiles128" else 64) > NUM_SMS
         inp = synthetic_inputs(env, 1, 30, True, seed=25)
         z, eps = _noise(26, cfg, 1, 1000, 30, env.obs_dim, env.act_dim)

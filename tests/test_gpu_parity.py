@@ -22,15 +22,16 @@ def _model(config, m_max=4, **kw):
     return build_model(config, m_max=m_max, **kw)
 
 
-@pytest.fixture(scope="module", params=["fp32", "tc3x-tiles", "tc3x-swapped"])
+@pytest.fixture(scope="module", params=["fp32", "tc3x-tiles", "tc3x-swapped", "tc3x-pairs"])
 def precision(request):
-    """fp32 FFMA path and both tensor-core kernels: 128-row tiles (rollout_tc.cu) and swapped operands (rollout_tcs.cu);
+    """fp32 FFMA path and the tensor-core kernels: 128-row tiles (rollout_tc.cu), swapped operands (rollout_tcs.cu) and the
+    CTA-pair variant of the latter (rollout_tcp.cu);
     the variant is forced through the engine's CADM_TC_VARIANT knob (cadm_set_option "tc_variant")."""
     import os
     name, _, variant = request.param.partition("-")
     old = os.environ.get("CADM_TC_VARIANT")
     if variant:
-        os.environ["CADM_TC_VARIANT"] = {"tiles": "1", "swapped": "2"}[variant]
+        os.environ["CADM_TC_VARIANT"] = {"tiles": "1", "swapped": "2", "pairs": "3"}[variant]
     yield name
     if old is None:
         os.environ.pop("CADM_TC_VARIANT", None)
