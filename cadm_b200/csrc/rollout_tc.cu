@@ -104,8 +104,10 @@ __host__ __device__ inline int pos_of_blk(int nkb, int kb) {
 // weight packing: [E, in, out] fp32 -> per member, per K16 block: [hi block | lo block], each N x 16 in the UMMA
 // K-major no-swizzle layout: byte(n, kk) = (kk / 8) * (16 N) + 16 n + 2 (kk % 8)
 // ------------------------------------------------------------------------------------------------
+struct PackPos { int pos[32]; };     // position of K16 block kb in the weight stream (pos_of_blk, computed once on the host:
+                                     // evaluating it per element made a set_weights() cost 1 ms, 88 us per layer)
 __global__ void pack_tc_kernel(unsigned char* dst, const float* src, int E, int in, int out, int col0, int nkb, int Npad,
-                               long long member_stride, long long layer_off, int clear, float wscale) {
+                               long long member_stride, long long layer_off, int clear, float wscale, const PackPos pp) {
     const long long per_member = (long long)nkb * Npad * 16;
     const long long total = (long long)E * per_member;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -121,7 +123,7 @@ __global__ void pack_tc_kernel(unsigned char* dst, const float* src, int E, int 
         const float w = valid ? src[((size_t)e * in + k) * out + ns] * wscale : 0.f;
         uint32_t hi, lo;
         tc::split2(w, 0.f, hi, lo);
-        unsigned char* blk = dst + e * member_stride + layer_off + (long long)pos_of_blk(nkb, kb) * (2 * Npad * 32);
+        unsigned char* blk = dst + e * member_stride + layer_off + (long long)pp.pos[kb] * (2 * Npad * 32);
         const int off = (kk >> 3) * (16 * Npad) + 16 * n + 2 * (kk & 7);
         *reinterpret_cast<unsigned short*>(blk + off) = (unsigned short)(hi & 0xffffu);
         *reinterpret_cast<unsigned short*>(blk + Npad * 32 + off) = (unsigned short)(lo & 0xffffu);
@@ -132,8 +134,11 @@ cudaError_t launch_pack_tc(unsigned char* dst, const float* src, int E, int in, 
                            long long member_stride, long long layer_off, int clear, cudaStream_t stream) {
     const float wscale = tc::kWScale;
     const long long total = (long long)E * nkb * Npad * 16;
+    if (nkb > 32) return cudaErrorInvalidConfiguration;
+    PackPos pp{};
+    for (int kb = 0; kb < nkb; ++kb) pp.pos[kb] = pos_of_blk(nkb, kb);
     pack_tc_kernel<<<(int)min((total + 255) / 256, (long long)2368), 256, 0, stream>>>(dst, src, E, in, out, col0, nkb, Npad,
-                                                                                       member_stride, layer_off, clear, wscale);
+                                                                                       member_stride, layer_off, clear, wscale, pp);
     return cudaGetLastError();
 }
 
