@@ -325,17 +325,22 @@ cudaError_t launch_rs_gather(const float* actions, const int* actions_int, const
 // context encoder (core/utils.py:400-407, 591-617): relu hidden layers, linear output; one CTA per (mi, e)
 // ------------------------------------------------------------------------------------------------
 
-// One CTA per (environment, member).  A layer is a mat-vec with 10^4..10^5 weights read once from L2: the k range is split
-// over the warps' lanes in groups (kSplit lanes per output unit, partial sums combined with shuffles) so that every thread
-// has several independent loads in flight instead of one 240-deep dependent FMA chain per output (which took ~130 us).
-// The summation order is fixed (per-lane serial, then a butterfly), so the result does not depend on the launch.
+// One CTA per (environment, member).  A layer is a mat-vec whose 10^4..10^5 weights are read exactly once, usually from HBM
+// (the planner's working set between two decisions does not keep them in L2), so the kernel is a latency problem: what counts
+// is how many independent loads are in flight.  Thread t owns FOUR consecutive outputs (one 16-byte load per weight row,
+// coalesced: a warp reads 512 contiguous bytes of a row) and every (512 / (out / 4))-th input row; eight rows are loaded
+// before the first FMA, i.e. 64 KB in flight per CTA.  The partial sums of the row groups are combined through shared memory
+// in a fixed order, so the result does not depend on the launch.  (The first version gave eight lanes one output each and
+// walked the rows four at a time: 30 dependent round trips to HBM per layer, 152 us per decision under a cold L2; this one
+// takes about a tenth.)  Layers whose width is not a multiple of four (the 10-wide output) take the scalar path.
 __global__ void __launch_bounds__(512) encoder_kernel(const EncoderParams Q) {
-    extern __shared__ float ebuf[];      // two ping-pong vectors of max width
+    extern __shared__ float ebuf[];      // two ping-pong vectors of max width, then the row-group partial sums [nrg][out]
     const int mi = blockIdx.x, e = blockIdx.y;
     int wmax = 0;
     for (int l = 0; l <= Q.n_layers; ++l) wmax = max(wmax, Q.dims[l]);
     float* x = ebuf;
     float* y = ebuf + wmax;
+    float* part = ebuf + 2 * wmax;       // 2048 floats
     const int no = Q.D * Q.K, na = Q.A * Q.K;
     for (int i = threadIdx.x; i < no + na; i += blockDim.x) {
         float v;
@@ -344,25 +349,59 @@ __global__ void __launch_bounds__(512) encoder_kernel(const EncoderParams Q) {
         x[i] = v;
     }
     __syncthreads();
-    constexpr int kSplit = 8;            // lanes per output unit
-    const int sub = threadIdx.x % kSplit, grp = threadIdx.x / kSplit, ngrp = blockDim.x / kSplit;
     for (int l = 0; l < Q.n_layers; ++l) {
         const int in = Q.dims[l], out = Q.dims[l + 1];
         const float* W = Q.W[l] + (size_t)e * in * out;
         const float* b = Q.b[l] + (size_t)e * out;
-        for (int j0 = 0; j0 < out; j0 += ngrp) {
-            const int j = j0 + grp;
-            float acc = 0.f;
-            if (j < out) {
-#pragma unroll 4
-                for (int i = sub; i < in; i += kSplit) acc = fmaf(x[i], __ldg(W + (size_t)i * out + j), acc);
-            }
+        const int ncol4 = out >> 2;
+        if ((out & 3) == 0 && ncol4 <= 512 && (512 / ncol4) * out <= 2048 && ((size_t)W & 15) == 0) {
+            const int nrg = 512 / ncol4;                         // row groups
+            const int cj = threadIdx.x % ncol4, rg = threadIdx.x / ncol4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rg < nrg) {
+                const float4* Wv = reinterpret_cast<const float4*>(W) + cj;
+                for (int k0 = rg; k0 < in; k0 += 8 * nrg) {
+                    float4 w[8];
 #pragma unroll
-            for (int o = kSplit / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (j < out && sub == 0) {
-                acc += b[j];
-                if (l < Q.n_layers - 1) acc = fmaxf(acc, 0.f);
-                y[j] = acc;
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = k0 + u * nrg;
+                        w[u] = k < in ? __ldg(Wv + (size_t)k * ncol4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = k0 + u * nrg;
+                        const float xk = k < in ? x[k] : 0.f;
+                        acc.x = fmaf(xk, w[u].x, acc.x); acc.y = fmaf(xk, w[u].y, acc.y);
+                        acc.z = fmaf(xk, w[u].z, acc.z); acc.w = fmaf(xk, w[u].w, acc.w);
+                    }
+                }
+                *reinterpret_cast<float4*>(part + rg * out + 4 * cj) = acc;
+            }
+            __syncthreads();
+            for (int j = threadIdx.x; j < out; j += blockDim.x) {
+                float sum = 0.f;
+                for (int r = 0; r < nrg; ++r) sum += part[r * out + j];
+                sum += b[j];
+                if (l < Q.n_layers - 1) sum = fmaxf(sum, 0.f);
+                y[j] = sum;
+            }
+        } else {
+            constexpr int kSplit = 8;            // lanes per output unit
+            const int sub = threadIdx.x % kSplit, grp = threadIdx.x / kSplit, ngrp = blockDim.x / kSplit;
+            for (int j0 = 0; j0 < out; j0 += ngrp) {
+                const int j = j0 + grp;
+                float acc = 0.f;
+                if (j < out) {
+#pragma unroll 8
+                    for (int i = sub; i < in; i += kSplit) acc = fmaf(x[i], __ldg(W + (size_t)i * out + j), acc);
+                }
+#pragma unroll
+                for (int o = kSplit / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (j < out && sub == 0) {
+                    acc += b[j];
+                    if (l < Q.n_layers - 1) acc = fmaxf(acc, 0.f);
+                    y[j] = acc;
+                }
             }
         }
         __syncthreads();
@@ -374,7 +413,7 @@ __global__ void __launch_bounds__(512) encoder_kernel(const EncoderParams Q) {
 cudaError_t launch_encoder(const EncoderParams& Q, cudaStream_t stream) {
     int wmax = 0;
     for (int l = 0; l <= Q.n_layers; ++l) wmax = max(wmax, Q.dims[l]);
-    encoder_kernel<<<dim3(Q.m, Q.E), 512, 2 * wmax * sizeof(float), stream>>>(Q);
+    encoder_kernel<<<dim3(Q.m, Q.E), 512, (2 * wmax + 2048) * sizeof(float), stream>>>(Q);
     return cudaGetLastError();
 }
 
