@@ -93,7 +93,23 @@ def trainer_done(model):
     model._trainer_version = getattr(model, "_params_version", 0)
 
 
-class EnsembleNLLTrainer:
+class IndexedFeed:
+    """The interface the fit loops drive (shared with native_trainer.NativeTrainer): the training and validation arrays are
+    handed over once per fit(), a minibatch is an index matrix [E, B].  A trainer that wants gathered batches -- the autograd
+    classes below, the recording doubles of the tests -- gets them through train_step() / evaluate() exactly as the reference's
+    session was fed (mlp_ensemble_cem_dynamics.py:262-283)."""
+
+    def begin_fit(self, train, valid, stats):
+        self._data, self._stats = (train, valid), stats
+
+    def train_step_idx(self, idx):
+        return self.train_step(*[a[idx] for a in self._data[0]], self._stats)
+
+    def evaluate_idx(self, idx, which=1):
+        return self.evaluate(*[a[idx] for a in self._data[which]], self._stats)
+
+
+class EnsembleNLLTrainer(IndexedFeed):
     """Parameters of the dynamics ensemble as torch leaves + the reference's loss and optimiser."""
 
     def __init__(self, dyn, env_name, deterministic, weight_decays, weight_decay_coeff, learning_rate, device="cpu",
@@ -173,16 +189,6 @@ class EnsembleNLLTrainer:
     def evaluate(self, bs_obs, bs_act, bs_delta, stats):
         out = self.losses(bs_obs, bs_act, bs_delta, stats)
         return float(out["mse_loss"]), float(out["recon_loss"])
-
-    # index-based interface shared with native_trainer.NativeTrainer: the datasets are handed over once per fit()
-    def begin_fit(self, train, valid, stats):
-        self._data, self._stats = (train, valid), stats
-
-    def train_step_idx(self, idx):
-        return self.train_step(*[a[idx] for a in self._data[0]], self._stats)
-
-    def evaluate_idx(self, idx, which=1):
-        return self.evaluate(*[a[idx] for a in self._data[which]], self._stats)
 
     def export(self, dyn):
         """Write the trained values back into the model's arrays (in place, float32)."""
@@ -281,7 +287,7 @@ def fit_ensemble(model, obs, act, obs_next, epochs=1000, valid_split_ratio=None,
 
 # ---------------------------------------------------------------------------------------------------------- CaDM
 
-class CaDMTrainer:
+class CaDMTrainer(IndexedFeed):
     """Context encoder + forward model (+ backward model when back_coeff > 0) with the joint loss of
     mlp_cadm_ensemble_cem_dynamics.py:266-317.  Member e of the encoder feeds member e of both models (:113-127, the
     bootstrap batch [E, B, .] goes through the encoder's batched matmul), and both models receive the SAME context
@@ -366,15 +372,6 @@ class CaDMTrainer:
     def evaluate(self, *batch_and_stats):
         out = self.losses(*batch_and_stats)
         return float(out["mse_loss"]), float(out["back_mse_loss"]), float(out["recon_loss"])
-
-    def begin_fit(self, train, valid, stats):
-        self._data, self._stats = (train, valid), stats
-
-    def train_step_idx(self, idx):
-        return self.train_step(*[a[idx] for a in self._data[0]], self._stats)
-
-    def evaluate_idx(self, idx, which=1):
-        return self.evaluate(*[a[idx] for a in self._data[which]], self._stats)
 
     def export(self, enc, dyn, back):
         g = lambda p: p.detach().to("cpu", torch.float32).numpy()

@@ -283,7 +283,10 @@ class _LegacyRng:
         return np.random.uniform(size=size)
 
 
-class _RecordingTrainer:
+from cadm_b200.dynamics.training import IndexedFeed
+
+
+class _RecordingTrainer(IndexedFeed):
     """Stands where the reference has its session: records what every training / validation step is fed and answers with the
     scripted losses of the recording."""
 
