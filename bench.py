@@ -45,13 +45,14 @@ def load_peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, src="fallback")
 
 
-def ncu_traffic(kernel_name):
+def ncu_traffic(kernel_name, config="C2", m=1):
     """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture of the same
-    workload (profiles/*_ncu_summary.csv, written by tools/ncu_summary.py); None when no capture of that kernel is there."""
+    workload (profiles/r<round>_<kernel>_<config>_m<m>_ncu_summary.csv, written by tools/ncu_summary.py, latest round first);
+    None when no capture of that kernel on that workload is there."""
     import csv
     import glob
     key = kernel_name.split("(")[0]
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.csv")), reverse=True):
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_{config}_m{m}_ncu_summary.csv")), reverse=True):
         try:
             rows = list(csv.reader(open(path)))
             hdr, units, vals = rows[0], rows[1], rows[2]
@@ -389,7 +390,7 @@ def run_engine(args, rank, world, local_rank):
     peaks = load_peaks()
     E, p, h = prim["E"], prim["p"], prim["h"]
     single_default = world == 1 and args.config == "C2" and args.m == 1 and not sweep
-    traffic, traffic_src = ncu_traffic(prim["kernel"]) if single_default else (None, None)
+    traffic, traffic_src = ncu_traffic(prim["kernel"], args.config, args.m) if (world == 1 and not sweep) else (None, None)
     name = WORKLOAD_NAMES[args.config] if not sweep else f"HalfCheetah PE-TS CEM sweep cell (ens={E}, part={p}, cand={n_primary}, horizon={h})"
     line = {
         "metric": METRIC, "value": prim["value"], "unit": UNIT, "n_gpus": world,
