@@ -33,6 +33,8 @@ struct RolloutParams {
     int row_mode;
     int rows_per_member;      // planner: q*m*n_local ; predict: B
     int rows_per_cta;
+    int row_lo, row_hi;       // the rows of every member THIS launch covers, [row_lo, row_hi); row_hi == 0: all of them.  The engine
+                              // may split a batch between two kernels (full waves of 128-row tiles + a remainder of small tiles)
     float max_torque;
     // padded dims of the packed fp32 weights
     int Kp0;                  // In rounded up to kChunkK

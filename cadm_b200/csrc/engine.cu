@@ -185,33 +185,70 @@ int run_rollout(Engine* E, RolloutParams& P, cudaStream_t s) {
             P.bpack = E->bpack_tc;
             P.bias_stride = E->bias_stride_tc;
             {
-                // Which tensor-core kernel, and for the swapped-operand one how many rows per tile: the launch time is
+                // Which tensor-core kernel(s), and for the swapped-operand one how many rows per tile: the launch time is
                 // (waves of tiles over the SMs) x (time of one wave), and one wave costs about the same for every workload of the
                 // reference architecture -- measured on B200 (profiles/r2_variant_sweep.log, us per launch at h = 30):
                 //   128-row tiles (rollout_tc.cu) 570,   swapped operands (rollout_tcs.cu) 238 / 293 / 375 for 32 / 48 / 64 rows.
-                // The model reproduces the measured launch times of C2 (m = 1, 4, 10), C3 (m = 2) and C4 to 3 %.
+                // Per row the 128-row kernel is the cheapest (4.5 us against 6.1 - 7.4) but only in FULL waves, so a large batch is
+                // split: k full waves of 128-row tiles, and the rows that would start a mostly empty wave go to one wave of the
+                // swapped kernel with small tiles (two launches, disjoint rows of every member).  The model reproduces the measured
+                // launch times of C2 (m = 1, 4, 10), C3 (m = 2) and C4 to 3 %.
                 const bool swapped_ok = E->Np16 <= 256 && E->NHp16 <= 128;
-                bool swapped = E->tc_variant == 2;
+                const int rows_pm = P.rows_per_member, sms = E->num_sms;
+                int rows_tc = E->tc_variant == 1 ? rows_pm : 0;           // rows of every member given to the 128-row kernel
                 int rows_pick = E->tcs_rows;
-                if (E->tc_variant == 0 && swapped_ok) {
-                    auto waves = [&](int rows) { return (P.E * ((P.rows_per_member + rows - 1) / rows) + E->num_sms - 1) / E->num_sms; };
-                    int best = waves(128) * 570;
-                    const int cost[3] = {238, 293, 375};
-                    for (int i = 0; i < 3; ++i) {
-                        const int c = waves(32 + 16 * i) * cost[i];
-                        if (c < best) { best = c; swapped = true; if (E->tcs_rows == 0) rows_pick = 32 + 16 * i; }
+                if (E->tc_variant == 2) rows_tc = 0;
+                if (E->tc_variant == 0) {
+                    rows_tc = rows_pm;
+                    if (swapped_ok) {
+                        auto waves = [&](int span, int rows) { return (P.E * ((span + rows - 1) / rows) + sms - 1) / sms; };
+                        const int cost[3] = {238, 293, 375};
+                        auto best_tcs = [&](int span, int& pick) {       // cheapest swapped launch over `span` rows per member
+                            int best = 1 << 30;
+                            for (int i = 0; i < 3; ++i) {
+                                if (E->tcs_rows != 0 && E->tcs_rows != 32 + 16 * i) continue;
+                                const int c = waves(span, 32 + 16 * i) * cost[i];
+                                if (c < best) { best = c; pick = 32 + 16 * i; }
+                            }
+                            return best;
+                        };
+                        int best = waves(rows_pm, 128) * 570;            // everything on 128-row tiles
+                        int pick = 32;
+                        const int all_tcs = best_tcs(rows_pm, pick);
+                        if (all_tcs < best) { best = all_tcs; rows_tc = 0; rows_pick = pick; }
+                        for (int k = 1; k <= 64; ++k) {                  // k full waves of 128-row tiles + the rest swapped
+                            const int tiles_pm = k * sms / P.E;
+                            const int r1 = tiles_pm * 128;
+                            if (tiles_pm < 1) continue;
+                            if (r1 >= rows_pm) break;
+                            int pk = 32;
+                            const int c = k * 570 + best_tcs(rows_pm - r1, pk);
+                            if (c < best) { best = c; rows_tc = r1; rows_pick = pk; }
+                        }
                     }
                 }
                 const int terms = E->precision == CADM_PREC_TC_3X ? 3 : 1;
                 if (E->tc_variant == 3) {
                     if (!tcp_supported(P, E->tcs_kps)) return fail(E, CADM_ERR_UNSUPPORTED, "tc_variant 3 (CTA pairs) covers the reference architecture only");
                     CU(E, launch_rollout_tcp(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_rows, E->num_sms, s, &E->kernel_name, E->trace ? E->dbg : nullptr));
-                } else if (swapped)
-                    CU(E, launch_rollout_tcs(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_kps, rows_pick, E->tcs_skew, E->num_sms, s,
-                                             &E->kernel_name, E->trace ? E->dbg : nullptr));
-                else
-                    CU(E, launch_rollout_tc(P, E->wimg, E->wimg_member_stride, terms, E->num_sms, s, &E->kernel_name,
-                                            E->trace ? E->dbg : nullptr));
+                } else {
+                    const char* n1 = nullptr;
+                    const char* n2 = nullptr;
+                    if (rows_tc > 0) {
+                        P.row_lo = 0; P.row_hi = rows_tc;
+                        CU(E, launch_rollout_tc(P, E->wimg, E->wimg_member_stride, terms, E->num_sms, s, &n1, E->trace ? E->dbg : nullptr));
+                    }
+                    if (rows_tc < rows_pm) {
+                        P.row_lo = rows_tc; P.row_hi = rows_pm;
+                        CU(E, launch_rollout_tcs(P, E->wimg_s, E->wimg_member_stride, terms, E->tcs_kps, rows_pick, E->tcs_skew, E->num_sms, s, &n2,
+                                                 (E->trace && rows_tc == 0) ? E->dbg : nullptr));
+                        if (rows_tc > 0) E->launches++;
+                    }
+                    P.row_lo = 0; P.row_hi = 0;
+                    E->kernel_name = (n1 && n2) ? (terms == 3 ? "rollout_tc_kernel(128-row tiles, full waves) + rollout_tcs_kernel(swapped operands, the rest), fp16 hi/lo x3"
+                                                              : "rollout_tc_kernel(128-row tiles, full waves) + rollout_tcs_kernel(swapped operands, the rest), f16 x1")
+                                                : (n1 ? n1 : n2);
+                }
             }
             break;
         default:

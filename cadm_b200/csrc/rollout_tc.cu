@@ -407,8 +407,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rollout_tc_kernel(const __grid_
 
         for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
             const int e = tile / T.tiles_per_member;
-            const int tile_row0 = (tile - e * T.tiles_per_member) * P.rows_per_cta;
-            const int nrows = min(P.rows_per_cta, P.rows_per_member - tile_row0);
+            const int tile_row0 = P.row_lo + (tile - e * T.tiles_per_member) * P.rows_per_cta;
+            const int nrows = min(P.rows_per_cta, P.row_hi - tile_row0);
             ptx::bar_sync(1, kEpiThreads);             // previous tile fully retired before its smem is reused
             for (int i = et; i < P.n_hidden * T.Np + T.NHp; i += kEpiThreads)      // hidden-layer biases pre-scaled by kXScale
                 bias[i] = P.bpack[(size_t)e * P.bias_stride + i] * (i < P.n_hidden * T.Np ? tc::kXScale : 1.0f);
@@ -659,9 +659,12 @@ cudaError_t launch_rollout_tc(RolloutParams P, const unsigned char* wimg, long l
     T.nkb0 = round_up(P.In, 16) / 16;
     T.nkbH = T.Np / 16;
     T.terms = terms;
-    int tiles = (P.rows_per_member + kTileRows - 1) / kTileRows;
-    P.rows_per_cta = (P.rows_per_member + tiles - 1) / tiles;            // balance the rows over the tiles
-    tiles = (P.rows_per_member + P.rows_per_cta - 1) / P.rows_per_cta;
+    if (P.row_hi <= 0) { P.row_lo = 0; P.row_hi = P.rows_per_member; }
+    const int span = P.row_hi - P.row_lo;                                 // rows of every member this launch covers
+    if (span < 1 || P.row_lo < 0 || P.row_hi > P.rows_per_member) return cudaErrorInvalidValue;
+    int tiles = (span + kTileRows - 1) / kTileRows;
+    P.rows_per_cta = (span + tiles - 1) / tiles;                          // balance the rows over the tiles
+    tiles = (span + P.rows_per_cta - 1) / P.rows_per_cta;
     T.tiles_per_member = tiles;
     T.total_tiles = tiles * P.E;
     for (int i = 0; i < T.nkb0; ++i) T.order0[i] = (unsigned char)blk_of_pos(T.nkb0, i);

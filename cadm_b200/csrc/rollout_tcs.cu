@@ -512,8 +512,8 @@ __global__ void __launch_bounds__(kSThreads, 1) rollout_tcs_kernel(const __grid_
 
         for (int tile = blockIdx.x; tile < T.total_tiles; tile += gridDim.x) {
             const int e = tile / T.tiles_per_member;
-            const int tile_row0 = (tile - e * T.tiles_per_member) * P.rows_per_cta;
-            const int nrows = min(P.rows_per_cta, P.rows_per_member - tile_row0);
+            const int tile_row0 = P.row_lo + (tile - e * T.tiles_per_member) * P.rows_per_cta;
+            const int nrows = min(P.rows_per_cta, P.row_hi - tile_row0);
             ptx::bar_sync(1, kSEpiThreads);             // previous tile fully retired before its smem is reused
             for (int i = et; i < P.n_hidden * T.Np + T.NHp; i += kSEpiThreads)      // hidden-layer biases pre-scaled by kXScale
                 bias[i] = P.bpack[(size_t)e * P.bias_stride + i] * (i < P.n_hidden * T.Np ? -tc::kLog2e : 1.0f);
@@ -942,14 +942,17 @@ cudaError_t launch_rollout_tcs(RolloutParams P, const unsigned char* wimg, long 
     const bool generic = (skew >> 28) & 1;     // diagnostic: force the table-driven MMA schedule
     T.nmt = T.Np > 128 ? 2 : 1;
     if (T.Np > 256 || T.NHp > 128 || kps < 1 || kps > kSMaxKps) return cudaErrorInvalidConfiguration;
-    int N = rows_override > 0 ? rows_override : tcs_pick_rows(P.rows_per_member, P.E, num_sms);
+    if (P.row_hi <= 0) { P.row_lo = 0; P.row_hi = P.rows_per_member; }
+    const int span = P.row_hi - P.row_lo;                       // rows of every member this launch covers
+    if (span < 1 || P.row_lo < 0 || P.row_hi > P.rows_per_member) return cudaErrorInvalidValue;
+    int N = rows_override > 0 ? rows_override : tcs_pick_rows(span, P.E, num_sms);
     N = min(kSMaxRows, max(16, round_up(N, 16)));
     // wide state vectors with 64-row tiles do not leave room for two weight stages: take narrower tiles (more of them)
     while (N > 16 && tcs_smem_layout(N, P.D, P.A, P.C, P.n_hidden, T.Np, T.NHp, T.Kcap, T.nkb0, kps, 2).total > 226 * 1024) N -= 16;
-    int tiles = (P.rows_per_member + N - 1) / N;
-    N = min(N, round_up((P.rows_per_member + tiles - 1) / tiles, 16));      // balance the rows over the tiles
-    P.rows_per_cta = min(N, (P.rows_per_member + tiles - 1) / tiles);
-    tiles = (P.rows_per_member + P.rows_per_cta - 1) / P.rows_per_cta;
+    int tiles = (span + N - 1) / N;
+    N = min(N, round_up((span + tiles - 1) / tiles, 16));      // balance the rows over the tiles
+    P.rows_per_cta = min(N, (span + tiles - 1) / tiles);
+    tiles = (span + P.rows_per_cta - 1) / P.rows_per_cta;
     T.N = N;
     T.tiles_per_member = tiles;
     T.total_tiles = tiles * P.E;

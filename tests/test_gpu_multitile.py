@@ -34,6 +34,7 @@ KERNELS = {
     "swapped32": ("tc3x", "2", "32"),
     "pairs32": ("tc3x", "3", "32"),
     "pairs64": ("tc3x", "3", "64"),
+    "auto": ("tc3x", None, None),            # the engine's choice: for these batches full waves of 128-row tiles + swapped small tiles
 }
 
 
@@ -135,6 +136,8 @@ def test_multi_tile_rollout_states_and_returns():
                                           eps.astype(np.float64), None, trace=True)
         pr, st = model.engine.rollout(inp["obs"], actions, None, eps, it=0, trace=True)
         pr, st = pr.cpu().numpy(), st.cpu().numpy()
+        if kernel == "auto":                              # 40 000 rows: two launches over disjoint rows of every member
+            assert "+" in model.engine.kernel_name, model.engine.kernel_name
         assert np.isfinite(st).all(), kernel
         assert rel_err(st, ref_st, axis=(1, 2, 3)) < TOL, kernel
         assert np.max(np.abs(pr - ref_ret)) / np.max(np.abs(ref_ret)) < TOL, kernel
@@ -167,7 +170,7 @@ def test_c4_full_decision():
     decision (context encoder, odd-iteration context pairing, 5 x 30 steps, top-50 of 1000, refit) on every kernel."""
     from cadm_b200.synth import synthetic_inputs
     ref = None
-    for kernel in ("tiles128", "swapped64", "pairs64", "fp32"):
+    for kernel in ("tiles128", "swapped64", "pairs64", "auto", "fp32"):
         model, env, cfg = _build("C4", kernel, m_max=1)
         assert cfg["candidates"] == 1000 and cfg["horizon"] == 30
         if kernel in ("tiles128", "swapped64"):
@@ -186,7 +189,7 @@ def test_c5_sweep_cells(n, p, h):
     """BASELINE.json configs[4]: the sweep's p = 100 and n = 5000 corners as decisions (short horizon, n / p kept)."""
     from cadm_b200.synth import synthetic_inputs
     ref = None
-    for kernel in ("tiles128", "swapped64"):
+    for kernel in ("tiles128", "swapped64", "auto"):
         model, env, cfg = _build("C2", kernel, m_max=1, horizon=h, candidates=n, particles=p)
         assert _tiles(cfg, 1, n, 128 if kernel == "tiles128" else 64) > NUM_SMS
         inp = synthetic_inputs(env, 1, h, False, seed=27)
