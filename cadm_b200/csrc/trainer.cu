@@ -363,6 +363,20 @@ int tfail(Trainer* T, int code, const std::string& msg) {
 
 Trainer* TH(void* h) { return reinterpret_cast<Trainer*>(h); }
 
+// Every entry point works on the device the handle was created on, whatever the caller's current device is, and leaves the
+// caller's device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 cudaError_t tmalloc(float** p, size_t n) {
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(float));
@@ -555,7 +569,7 @@ int cadm_train_create(const CadmTrainConfig* cfg, void** handle) {
 int cadm_train_destroy(void* handle) {
     Trainer* T = TH(handle);
     if (!T) return CADM_OK;
-    cudaSetDevice(T->device);
+    DeviceGuard guard(T->device);
     cudaDeviceSynchronize();
     free_net_ws(T->enc); free_net_ws(T->fwd); free_net_ws(T->back);
     cudaFree(T->dz0); cudaFree(T->dz1); cudaFree(T->dctx); cudaFree(T->idx_dev);
@@ -578,6 +592,7 @@ int64_t cadm_train_launch_count(void* handle) { return handle ? TH(handle)->laun
 int cadm_train_set_params(void* handle, const float* flat_host, int64_t n) {
     Trainer* T = TH(handle);
     if (!T || !flat_host || n != T->n_params) return tfail(T, CADM_ERR_ARG, "cadm_train_set_params: wrong length");
+    DeviceGuard guard(T->device);
     TCU(T, cudaMemcpy(T->params, flat_host, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
     return CADM_OK;
 }
@@ -585,6 +600,7 @@ int cadm_train_set_params(void* handle, const float* flat_host, int64_t n) {
 int cadm_train_get_params(void* handle, float* flat_host, int64_t n) {
     Trainer* T = TH(handle);
     if (!T || !flat_host || n != T->n_params) return tfail(T, CADM_ERR_ARG, "cadm_train_get_params: wrong length");
+    DeviceGuard guard(T->device);
     TCU(T, cudaStreamSynchronize(T->stream));
     TCU(T, cudaMemcpy(flat_host, T->params, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     return CADM_OK;
@@ -593,6 +609,7 @@ int cadm_train_get_params(void* handle, float* flat_host, int64_t n) {
 int cadm_train_get_grads(void* handle, float* flat_host, int64_t n) {
     Trainer* T = TH(handle);
     if (!T || !flat_host || n != T->n_params) return tfail(T, CADM_ERR_ARG, "cadm_train_get_grads: wrong length");
+    DeviceGuard guard(T->device);
     TCU(T, cudaStreamSynchronize(T->stream));
     TCU(T, cudaMemcpy(flat_host, T->grads, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     return CADM_OK;
@@ -601,6 +618,7 @@ int cadm_train_get_grads(void* handle, float* flat_host, int64_t n) {
 int cadm_train_adam_state(void* handle, int32_t set, float* m_host, float* v_host, int64_t n, int64_t* t_inout) {
     Trainer* T = TH(handle);
     if (!T || !m_host || !v_host || !t_inout || n != T->n_params) return tfail(T, CADM_ERR_ARG, "cadm_train_adam_state: wrong length");
+    DeviceGuard guard(T->device);
     TCU(T, cudaStreamSynchronize(T->stream));
     const size_t bytes = (size_t)n * sizeof(float);
     if (set) {
@@ -618,6 +636,7 @@ int cadm_train_adam_state(void* handle, int32_t set, float* m_host, float* v_hos
 int cadm_train_set_norm(void* handle, const float* const* stats_host, int32_t count) {
     Trainer* T = TH(handle);
     if (!T || !stats_host) return tfail(T, CADM_ERR_ARG, "cadm_train_set_norm: null argument");
+    DeviceGuard guard(T->device);
     const int need = T->has_back ? 12 : (T->has_enc ? 10 : 6);
     if (count < need) return tfail(T, CADM_ERR_ARG, "cadm_train_set_norm: not enough statistics for this model");
     const int sizes[12] = {T->P, T->P, T->A, T->A, T->D, T->D, T->D * T->K, T->D * T->K, T->A * T->K, T->A * T->K, T->D, T->D};
@@ -633,6 +652,7 @@ int cadm_train_set_dataset(void* handle, int32_t which, int64_t rows, const floa
                            const float* obs_next_host, const float* back_delta_host, const float* cp_obs_host, const float* cp_act_host) {
     Trainer* T = TH(handle);
     if (!T || which < 0 || which > 1 || rows < 0) return tfail(T, CADM_ERR_ARG, "cadm_train_set_dataset: bad argument");
+    DeviceGuard guard(T->device);
     if (rows > 0 && (!obs_host || !act_host || !delta_host)) return tfail(T, CADM_ERR_ARG, "cadm_train_set_dataset: obs / act / delta are required");
     if (rows > 0 && T->has_enc && (!cp_obs_host || !cp_act_host)) return tfail(T, CADM_ERR_ARG, "cadm_train_set_dataset: the CaDM model needs cp_obs / cp_act");
     if (rows > 0 && T->has_back && (!obs_next_host || !back_delta_host)) return tfail(T, CADM_ERR_ARG, "cadm_train_set_dataset: the backward model needs obs_next / back_delta");
@@ -665,7 +685,7 @@ int cadm_train_step(void* handle, int32_t which, const int32_t* idx_host, int32_
     if (!T->have_norm) return tfail(T, CADM_ERR_STATE, "cadm_train_step: cadm_train_set_norm first");
     Trainer::DS& d = T->ds[which];
     if (d.rows < 1) return tfail(T, CADM_ERR_STATE, "cadm_train_step: cadm_train_set_dataset first");
-    cudaSetDevice(T->device);
+    DeviceGuard guard(T->device);
     const long long R = (long long)T->E * B;
     for (long long i = 0; i < R; ++i)
         if (idx_host[i] < 0 || idx_host[i] >= d.rows) return tfail(T, CADM_ERR_ARG, "cadm_train_step: index outside the dataset");
