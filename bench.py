@@ -395,7 +395,8 @@ def run_engine(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": prim["value"], "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": prim["ms_per_step"], "higher_is_better": True,
-        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        # the label follows the requested mode at every N (at N = 1 both modes are the same run), so the driver's 1 -> 8 series is one mode
+        "scaling": "weak" if (args.scaling == "weak" and not sweep) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name + f", m={args.m}" + (f", n={n_primary} sharded {world} x {n_primary // world}" if world > 1 else ""),
                    "scaling": ("strong: the named config's candidates split over the GPUs" if strong else
                                f"weak: {base_n} candidates per GPU (n = {n_primary})") if world > 1 else "single GPU",
