@@ -389,7 +389,6 @@ def run_engine(args, rank, world, local_rank):
         return
     peaks = load_peaks()
     E, p, h = prim["E"], prim["p"], prim["h"]
-    single_default = world == 1 and args.config == "C2" and args.m == 1 and not sweep
     traffic, traffic_src = ncu_traffic(prim["kernel"], args.config, args.m) if (world == 1 and not sweep) else (None, None)
     name = WORKLOAD_NAMES[args.config] if not sweep else f"HalfCheetah PE-TS CEM sweep cell (ens={E}, part={p}, cand={n_primary}, horizon={h})"
     line = {
