@@ -319,7 +319,8 @@ class PlannerEngine:
         self.cfg.precision = precision
 
     def set_option(self, name: str, value: int):
-        """cadm_set_option: "tc_variant" (0 auto / 1 row tiles / 2 swapped operands), "tcs_rows", "tcs_kps"."""
+        """cadm_set_option: "tc_variant" (0 auto / 1 row tiles / 2 swapped operands / 3 CTA pairs), "tcs_rows", "tcs_kps", "pdl",
+        "trace", "env_offset", "peer_timeout_ms", "peer_clear_timeout" (include/cadm_b200.h)."""
         self._chk(self.lib.cadm_set_option(self._h, name.encode(), int(value)))
 
     # ------------------------------------------------------------------ instrumentation

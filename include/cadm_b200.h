@@ -227,7 +227,9 @@ int cadm_selftest_tcs_gemm(const float* X, const float* W, int32_t rows, int32_t
                            float* out, void* stream);
 
 /* Tuning knobs of the tensor-core path (the defaults are what bench.py measures):
- *   "tc_variant"  0 = pick by batch size, 1 = 128-row tiles (rollout_tc.cu), 2 = swapped operands (rollout_tcs.cu)
+ *   "tc_variant"  0 = pick by the measured wave-cost model (all rows on one kernel, or full waves of 128-row tiles + one wave of
+ *                 small swapped-operand tiles for the rest: two launches), 1 = 128-row tiles (rollout_tc.cu), 2 = swapped
+ *                 operands (rollout_tcs.cu), 3 = CTA pairs (rollout_tcp.cu: an experiment, slower; reference architecture only)
  *   "tcs_rows"    rows per tile of the swapped kernel: 0 = pick, else 16 / 32 / 48 / 64
  *   "tcs_kps"     K16 blocks per weight stage of the swapped kernel's image, 1..4 (before cadm_plan_set_weights)
  *   "tcs_skew"    start-delay step in cycles that de-phases the CTAs of the swapped kernel (0 = off)
@@ -236,6 +238,8 @@ int cadm_selftest_tcs_gemm(const float* X, const float* W, int32_t rows, int32_t
  *   "env_offset"  index of this engine's first environment in a larger, environment-sharded decision: added to the local
  *                 environment index in every Philox counter, so that a block of environments planned alone draws the same
  *                 numbers as inside the whole decision (cadm_b200/parallel.py EnvShardedPlanner)
+ *   "pdl"         0 = launch the sample -> rollout -> refit chain without programmatic dependent launch (process-wide; also
+ *                 CADM_PDL=0); default 1: the next kernel's prologue runs under its predecessor
  *   "peer_timeout_ms"     bound of the device-side wait for a peer's slice (fused all-gather), default 30000
  *   "peer_clear_timeout"  forget a reported peer timeout (after the caller has re-synchronised the ranks) */
 int cadm_set_option(void* handle, const char* name, int32_t value);
