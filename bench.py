@@ -221,7 +221,7 @@ def measure_leg(args, rank, world, local_rank, config, m, n_total, particles, sh
 
     dev = torch.device("cuda", local_rank)
     by_env = sharding == "envs"
-    model, env, cfg = build_model(config, m_max=max(m, 1), candidates=n_total, particles=particles or None,
+    model, env, cfg = build_model(config, m_max=max(m, 1), candidates=n_total, particles=particles or None, trained_like=not args.random_init_logvar,
                                   rank=0 if by_env else rank, world=1 if by_env else world, precision=args.precision, device=dev)
     eng = model.engine
     if by_env:
@@ -400,6 +400,8 @@ def run_engine(args, rank, world, local_rank):
                    "scaling": ("strong: the named config's candidates split over the GPUs" if strong else
                                f"weak: {base_n} candidates per GPU (n = {n_primary})") if world > 1 else "single GPU",
                    "precision": args.precision, "kernel": prim["kernel"],
+                   "weights": "random init of the reference (core/utils.py:636-641), " + ("b_logvar = 0 (noise-dominated rollouts)" if args.random_init_logvar
+                                                                                          else "b_logvar = -6 (trained-like: small sampled noise; SURVEY 8d)"),
                    "l2": "flushed between steps (256 MiB write outside the timed events); weights (2.7 MB) are L2-resident by design within a step",
                    "kernel_timing": "roofline.launch_ms: CUDA events around every rollout launch, in a second pass over the same K decisions "
                                     "(an event between kernels serialises the programmatic-dependent-launch chain the timed pass runs with)",
@@ -442,6 +444,8 @@ def main():
                     help="N > 1: which leg is the line's `value` -- weak = the config's candidate count PER GPU, strong = the named "
                          "config split over the GPUs; the other leg, C4 strong and the environment-sharded leg go under `legs`")
     ap.add_argument("--no-extra-legs", action="store_true", help="N > 1: only the primary leg")
+    ap.add_argument("--random-init-logvar", action="store_true",
+                    help="keep the reference's random-init log-variance head (b_logvar = 0) instead of the trained-like b_logvar = -6 (SURVEY 8d: report both)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cadm_b200" else args.warmup
 
